@@ -1,0 +1,19 @@
+// Host build of american_monte_carlo_b200/csrc/lsm_solve.h for the CPU-only test tier.
+// TEST INFRASTRUCTURE: compiled by tests/conftest.py into tests/native/_build/, never shipped,
+// never linked into libamc.so.  It lets `pytest -m "not gpu"` compare the device solver's source
+// with numpy.linalg.lstsq without a GPU.
+#include "../../american_monte_carlo_b200/csrc/lsm_solve.h"
+
+extern "C" int amc_test_lsm_solve(int degree, int basis, int scaling, double scaling_factor, double n_paths,
+                                  const double* h, const double* g, double y_scale, double mu_ref,
+                                  double sigma_ref, double* gamma, double* beta, double* sv, double* stats,
+                                  int* info) {
+    if (degree < 0 || degree > amc::kMaxDegree) return 1;
+    amc::SolveSpec spec{degree, basis, scaling, scaling_factor, n_paths};
+    amc::SolveResult res;
+    amc::lsm_solve(spec, h, g, y_scale, mu_ref, sigma_ref, &res);
+    for (int i = 0; i <= degree; ++i) { gamma[i] = res.gamma[i]; beta[i] = res.beta[i]; sv[i] = res.sv[i]; }
+    stats[0] = res.mean_x; stats[1] = res.std_x;
+    info[0] = res.rank; info[1] = res.k_internal; info[2] = res.sweeps;
+    return 0;
+}
