@@ -1,0 +1,872 @@
+// C ABI of libamc (see include/amc.h): contexts, device-resident path sets, the backward sweep driver and the
+// small array ops kept for API parity with /root/reference/american_monte_carlo.py.
+//
+// One process per GPU.  The sweep is a chain of (fused decide+moments launch) -> (solve launch) pairs on one
+// stream with no host synchronisation inside; multi-GPU inserts one NCCL all-reduce of <= 31 doubles between
+// the partial-sum reduction and the solve of every step (NCCL is dlopen'ed lazily: single-GPU use needs no
+// NCCL at all, and under torch the already-loaded libnccl.so.2 is reused).
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>      // types and enums only: the library is resolved at run time
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/amc.h"
+#include "kernels.h"
+
+using namespace amc;
+
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(AMC_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* amc_last_error(void) { return g_err; }
+extern "C" int amc_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, resolved lazily
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.handle) return AMC_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // torch's copy, if the process has one
+    const char* env = getenv("AMC_NCCL_LIB");
+    if (!h && env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(AMC_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                          \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                                                    \
+    if (!g_nccl.field) return fail(AMC_ERR_NCCL, "libnccl.so.2 lacks symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(AllGather, "ncclAllGather")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return AMC_OK;
+}
+
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess)                                                                            \
+            return fail(AMC_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct amc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    // grow-only scratch (one pricing call at a time per context)
+    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc;
+    std::vector<cudaEvent_t> events;
+    int grid_cache[2][AMC_MAX_K];
+};
+
+struct amc_paths {
+    amc_ctx* ctx = nullptr;
+    void* S = nullptr;
+    int64_t ld = 0, n_local = 0, n_global = 0;
+    int n_steps = 0, dtype = 0;
+    size_t bytes = 0;
+    std::vector<double> mu, sigma;      // per-column affine maps
+};
+
+static int ensure(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return AMC_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes < 256 ? 256 : bytes;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return AMC_OK;
+}
+
+static size_t elem_size(int dtype) { return dtype == AMC_F32 ? 4 : 8; }
+static const void* column(const amc_paths* p, int t) {
+    return (const char*)p->S + (size_t)t * (size_t)p->ld * elem_size(p->dtype);
+}
+
+extern "C" int amc_ctx_create(int device, void* stream, amc_ctx** out) {
+    if (!out) return fail(AMC_ERR_VALUE, "amc_ctx_create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(AMC_ERR_CUDA, "amc_ctx_create: no CUDA device (%s); libamc has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(AMC_ERR_VALUE, "amc_ctx_create: device %d of %d", device, count);
+    CU(cudaSetDevice(device));
+    amc_ctx* c = new amc_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->total_mem = prop.totalGlobalMem;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < AMC_MAX_K; ++j) c->grid_cache[i][j] = 0;
+    *out = c;
+    return AMC_OK;
+}
+
+extern "C" int amc_ctx_destroy(amc_ctx* c) {
+    if (!c) return AMC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
+    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return AMC_OK;
+}
+
+extern "C" int amc_ctx_sync(amc_ctx* c) {
+    if (!c) return fail(AMC_ERR_VALUE, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_ctx_device_info(amc_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
+    if (!c) return fail(AMC_ERR_VALUE, "null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (total_mem) *total_mem = (int64_t)c->total_mem;
+    return AMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int amc_comm_unique_id(char id[128]) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId uid;
+    NC(g_nccl.GetUniqueId(&uid));
+    memcpy(id, uid.internal, 128);
+    return AMC_OK;
+}
+
+extern "C" int amc_comm_init(amc_ctx* c, int world_size, int rank, const char id[128]) {
+    if (!c) return fail(AMC_ERR_VALUE, "null context");
+    if (world_size < 1 || rank < 0 || rank >= world_size)
+        return fail(AMC_ERR_VALUE, "amc_comm_init: rank %d of %d", rank, world_size);
+    if (c->comm) return fail(AMC_ERR_STATE, "amc_comm_init: communicator already initialised");
+    if (world_size == 1) { c->world = 1; c->rank = 0; return AMC_OK; }
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, world_size, uid, rank));
+    c->world = world_size;
+    c->rank = rank;
+    return AMC_OK;
+}
+
+extern "C" int amc_comm_info(amc_ctx* c, int* world_size, int* rank) {
+    if (!c) return fail(AMC_ERR_VALUE, "null context");
+    if (world_size) *world_size = c->world;
+    if (rank) *rank = c->rank;
+    return AMC_OK;
+}
+
+extern "C" int amc_comm_allreduce_host(amc_ctx* c, double* buf, int n) {
+    if (!c || !buf || n < 0) return fail(AMC_ERR_VALUE, "amc_comm_allreduce_host: bad argument");
+    if (c->world == 1 || n == 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure(c->misc, (size_t)n * 8);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->misc.p, buf, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(c->misc.p, c->misc.p, (size_t)n, ncclFloat64, ncclSum, c->comm, c->stream));
+    CU(cudaMemcpyAsync(buf, c->misc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// paths
+static int paths_alloc(amc_ctx* c, int n_steps, int64_t n_local, int64_t n_global, int dtype, amc_paths** out) {
+    if (!c || !out) return fail(AMC_ERR_VALUE, "null argument");
+    if (n_steps < 0 || n_local < 0 || n_global < n_local)
+        return fail(AMC_ERR_VALUE, "bad path-set shape: n_time_steps=%d n_paths_local=%lld n_paths_global=%lld", n_steps,
+                    (long long)n_local, (long long)n_global);
+    if (dtype != AMC_F64 && dtype != AMC_F32) return fail(AMC_ERR_VALUE, "unknown dtype %d", dtype);
+    CU(cudaSetDevice(c->device));
+    amc_paths* p = new amc_paths();
+    p->ctx = c;
+    p->n_steps = n_steps;
+    p->n_local = n_local;
+    p->n_global = n_global;
+    p->dtype = dtype;
+    p->ld = padded_len(n_local > 0 ? n_local : 1);
+    p->bytes = (size_t)p->ld * (size_t)(n_steps + 1) * elem_size(dtype);
+    cudaError_t e = cudaMalloc(&p->S, p->bytes);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(AMC_ERR_CUDA, "cudaMalloc of %zu bytes for the path matrix failed: %s", p->bytes, cudaGetErrorString(e));
+    }
+    p->mu.assign(n_steps + 1, 0.0);
+    p->sigma.assign(n_steps + 1, 1.0);
+    *out = p;
+    return AMC_OK;
+}
+
+// GBM moments: E S_t = S0 e^{rt}, Var S_t = S0^2 e^{2rt} (e^{sigma^2 t} - 1).  Any centre/scale is valid for the
+// internal standardisation; the analytic ones are deterministic and independent of the number of GPUs.
+static void analytic_maps(amc_paths* p, double S0, double r, double sigma, double T) {
+    const int n = p->n_steps;
+    for (int t = 0; t <= n; ++t) {
+        const double tt = n > 0 ? T * (double)t / (double)n : 0.0;
+        const double m = S0 * exp(r * tt);
+        const double v = expm1(sigma * sigma * tt);
+        double sd = m * sqrt(v > 0.0 ? v : 0.0);
+        p->mu[t] = m;
+        p->sigma[t] = (sd > 1e-12 * fabs(m) && sd > 0.0 && isfinite(sd)) ? sd : 1.0;
+    }
+}
+
+static GbmParams gbm_params(double S0, double r, double sigma, double T, int n) {
+    GbmParams g;
+    const double dt = T / (double)n;                       // amc.py:73
+    g.S0 = S0;
+    g.drift = (r - 0.5 * sigma * sigma) * dt;              // amc.py:75
+    g.vol = sigma * sqrt(dt);
+    return g;
+}
+
+extern "C" int amc_paths_generate(amc_ctx* c, double S0, double r, double sigma, double T, int n_time_steps,
+                                  int64_t n_paths_local, int64_t path_offset, int64_t n_paths_global, int dtype,
+                                  uint64_t seed, amc_paths** out) {
+    if (n_time_steps < 1) return fail(AMC_ERR_VALUE, "n_time_steps must be >= 1");
+    amc_paths* p = nullptr;
+    int rc = paths_alloc(c, n_time_steps, n_paths_local, n_paths_global, dtype, &p);
+    if (rc) return rc;
+    if (n_paths_local > 0) {
+        cudaError_t e = launch_generate_philox(dtype, p->S, p->ld, n_time_steps, n_paths_local, path_offset,
+                                               gbm_params(S0, r, sigma, T, n_time_steps), seed, c->sm_count, c->stream);
+        if (e != cudaSuccess) {
+            amc_paths_free(p);
+            return fail(AMC_ERR_CUDA, "philox path kernel launch: %s", cudaGetErrorString(e));
+        }
+    }
+    analytic_maps(p, S0, r, sigma, T);
+    *out = p;
+    return AMC_OK;
+}
+
+static int from_normals_impl(amc_ctx* c, const double* Z, bool z_on_device, double S0, double r, double sigma, double T,
+                             int n_time_steps, int64_t n_local, int64_t n_global, int dtype, amc_paths** out) {
+    if (n_time_steps < 1) return fail(AMC_ERR_VALUE, "n_time_steps must be >= 1");
+    if (!Z && n_local > 0) return fail(AMC_ERR_VALUE, "Z is null");
+    amc_paths* p = nullptr;
+    int rc = paths_alloc(c, n_time_steps, n_local, n_global, dtype, &p);
+    if (rc) return rc;
+    if (n_local > 0) {
+        const double* Zd = Z;
+        if (!z_on_device) {
+            const size_t zb = (size_t)n_local * (size_t)n_time_steps * 8;
+            rc = ensure(c->stage, zb);
+            if (rc) { amc_paths_free(p); return rc; }
+            cudaError_t e = cudaMemcpyAsync(c->stage.p, Z, zb, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) { amc_paths_free(p); return fail(AMC_ERR_CUDA, "H2D of normals: %s", cudaGetErrorString(e)); }
+            Zd = (const double*)c->stage.p;
+        }
+        cudaError_t e = launch_from_normals(dtype, Zd, p->S, p->ld, n_time_steps, n_local,
+                                            gbm_params(S0, r, sigma, T, n_time_steps), c->stream);
+        if (e != cudaSuccess) { amc_paths_free(p); return fail(AMC_ERR_CUDA, "normals path kernel launch: %s", cudaGetErrorString(e)); }
+    }
+    analytic_maps(p, S0, r, sigma, T);
+    *out = p;
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_from_normals(amc_ctx* c, const double* Z, double S0, double r, double sigma, double T,
+                                      int n_time_steps, int64_t n_paths_local, int64_t n_paths_global, int dtype,
+                                      amc_paths** out) {
+    return from_normals_impl(c, Z, false, S0, r, sigma, T, n_time_steps, n_paths_local, n_paths_global, dtype, out);
+}
+
+extern "C" int amc_paths_from_normals_dev(amc_ctx* c, const double* Z_dev, double S0, double r, double sigma, double T,
+                                          int n_time_steps, int64_t n_paths_local, int64_t n_paths_global, int dtype,
+                                          amc_paths** out) {
+    return from_normals_impl(c, Z_dev, true, S0, r, sigma, T, n_time_steps, n_paths_local, n_paths_global, dtype, out);
+}
+
+// measured maps for adopted matrices: per-column (count, mean, M2), merged over chunks and ranks in fixed order
+static int measured_maps(amc_ctx* c, amc_paths* p) {
+    const int ncol = p->n_steps + 1;
+    const int n_chunks = 64;
+    std::vector<double> cnt(ncol, 0.0), mean(ncol, 0.0), m2(ncol, 0.0);
+    if (p->n_local > 0) {
+        int rc = ensure(c->misc, (size_t)ncol * (n_chunks * 2 + 1) * 8);
+        if (rc) return rc;
+        double* partial = (double*)c->misc.p;
+        double* shift = partial + (size_t)ncol * n_chunks * 2;
+        CU(launch_column_stats(p->dtype, p->S, p->ld, ncol, p->n_local, n_chunks, partial, shift, c->stream));
+        std::vector<double> h((size_t)ncol * (n_chunks * 2 + 1));
+        CU(cudaMemcpyAsync(h.data(), partial, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int t = 0; t < ncol; ++t) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int k = 0; k < n_chunks; ++k) {
+                s1 += h[((size_t)t * n_chunks + k) * 2];
+                s2 += h[((size_t)t * n_chunks + k) * 2 + 1];
+            }
+            const double n = (double)p->n_local;
+            const double sh = h[(size_t)ncol * n_chunks * 2 + t];
+            const double m1 = s1 / n;
+            double var = s2 / n - m1 * m1;
+            if (var < 0.0) var = 0.0;
+            cnt[t] = n;
+            mean[t] = sh + m1;
+            m2[t] = var * n;
+        }
+    }
+    if (c->world > 1) {
+        // all-gather (count, mean, M2) triples and merge in rank order (Chan et al. pairwise update)
+        const size_t per = (size_t)ncol * 3;
+        int rc = ensure(c->misc, per * 8 * (size_t)(c->world + 1));
+        if (rc) return rc;
+        std::vector<double> mine(per);
+        for (int t = 0; t < ncol; ++t) { mine[3 * t] = cnt[t]; mine[3 * t + 1] = mean[t]; mine[3 * t + 2] = m2[t]; }
+        double* send = (double*)c->misc.p;
+        double* recv = send + per;
+        CU(cudaMemcpyAsync(send, mine.data(), per * 8, cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllGather(send, recv, per, ncclFloat64, c->comm, c->stream));
+        std::vector<double> all(per * c->world);
+        CU(cudaMemcpyAsync(all.data(), recv, all.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int t = 0; t < ncol; ++t) {
+            double n = 0.0, m = 0.0, q = 0.0;
+            for (int rk = 0; rk < c->world; ++rk) {
+                const double nb = all[rk * per + 3 * t], mb = all[rk * per + 3 * t + 1], qb = all[rk * per + 3 * t + 2];
+                if (nb <= 0.0) continue;
+                const double tot = n + nb, dlt = mb - m;
+                q = q + qb + dlt * dlt * n * nb / tot;
+                m = m + dlt * nb / tot;
+                n = tot;
+            }
+            cnt[t] = n; mean[t] = m; m2[t] = q;
+        }
+    }
+    for (int t = 0; t < ncol; ++t) {
+        const double sd = cnt[t] > 0.0 ? sqrt(m2[t] / cnt[t]) : 0.0;
+        p->mu[t] = mean[t];
+        p->sigma[t] = (sd > 1e-12 * fabs(mean[t]) && sd > 0.0 && isfinite(sd)) ? sd : 1.0;
+    }
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_from_host(amc_ctx* c, const double* S, int n_time_steps, int64_t n_paths_local,
+                                   int64_t n_paths_global, int dtype, amc_paths** out) {
+    if (!S && n_paths_local > 0) return fail(AMC_ERR_VALUE, "S is null");
+    amc_paths* p = nullptr;
+    int rc = paths_alloc(c, n_time_steps, n_paths_local, n_paths_global, dtype, &p);
+    if (rc) return rc;
+    if (n_paths_local > 0) {
+        const size_t sb = (size_t)n_paths_local * (size_t)(n_time_steps + 1) * 8;
+        rc = ensure(c->stage, sb);
+        if (rc) { amc_paths_free(p); return rc; }
+        cudaError_t e = cudaMemcpyAsync(c->stage.p, S, sb, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess)
+            e = launch_transpose_in(dtype, (const double*)c->stage.p, p->S, p->ld, n_time_steps + 1, n_paths_local, c->stream);
+        if (e != cudaSuccess) { amc_paths_free(p); return fail(AMC_ERR_CUDA, "adopting host paths: %s", cudaGetErrorString(e)); }
+    }
+    rc = measured_maps(c, p);
+    if (rc) { amc_paths_free(p); return rc; }
+    *out = p;
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_free(amc_paths* p) {
+    if (!p) return AMC_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->S) cudaFree(p->S);
+    delete p;
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_info(const amc_paths* p, int64_t* n_paths_local, int64_t* n_paths_global, int* n_time_steps,
+                              int* dtype, int64_t* bytes_on_device) {
+    if (!p) return fail(AMC_ERR_VALUE, "null paths");
+    if (n_paths_local) *n_paths_local = p->n_local;
+    if (n_paths_global) *n_paths_global = p->n_global;
+    if (n_time_steps) *n_time_steps = p->n_steps;
+    if (dtype) *dtype = p->dtype;
+    if (bytes_on_device) *bytes_on_device = (int64_t)p->bytes;
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_column(const amc_paths* p, int t, double* out) {
+    if (!p || !out) return fail(AMC_ERR_VALUE, "null argument");
+    if (t < 0 || t > p->n_steps) return fail(AMC_ERR_VALUE, "column %d out of range 0..%d", t, p->n_steps);
+    if (p->n_local == 0) return AMC_OK;
+    amc_ctx* c = p->ctx;
+    CU(cudaSetDevice(c->device));
+    if (p->dtype == AMC_F64) {
+        CU(cudaMemcpyAsync(out, column(p, t), (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        int rc = ensure(c->misc, (size_t)p->n_local * 8);
+        if (rc) return rc;
+        CU(launch_column_to_f64(p->dtype, column(p, t), p->n_local, (double*)c->misc.p, c->stream));
+        CU(cudaMemcpyAsync(out, c->misc.p, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_rows(const amc_paths* p, int64_t p0, int64_t p1, double* out) {
+    if (!p || !out) return fail(AMC_ERR_VALUE, "null argument");
+    if (p0 < 0 || p1 < p0 || p1 > p->n_local)
+        return fail(AMC_ERR_VALUE, "rows [%lld, %lld) out of range 0..%lld", (long long)p0, (long long)p1, (long long)p->n_local);
+    if (p1 == p0) return AMC_OK;
+    amc_ctx* c = p->ctx;
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)(p1 - p0) * (size_t)(p->n_steps + 1) * 8;
+    int rc = ensure(c->misc, bytes);
+    if (rc) return rc;
+    CU(launch_gather_rows(p->dtype, p->S, p->ld, p->n_steps + 1, p0, p1, (double*)c->misc.p, c->stream));
+    CU(cudaMemcpyAsync(out, c->misc.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_paths_column_maps(const amc_paths* p, double* mu, double* sigma) {
+    if (!p) return fail(AMC_ERR_VALUE, "null paths");
+    for (int t = 0; t <= p->n_steps; ++t) {
+        if (mu) mu[t] = p->mu[t];
+        if (sigma) sigma[t] = p->sigma[t];
+    }
+    return AMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward sweep
+static int check_spec(const amc_lsm_spec* s) {
+    if (!s) return fail(AMC_ERR_VALUE, "null spec");
+    if (s->basis < 0 || s->basis > AMC_BASIS_LAGUERRE)
+        return fail(AMC_ERR_VALUE, "Unknown basis type id %d. Use 'Power', 'Chebyshev', or 'Legendre'.", s->basis);
+    if (s->degree < 0 || s->degree > AMC_MAX_DEGREE)
+        return fail(AMC_ERR_VALUE, "degree %d outside 0..%d", s->degree, AMC_MAX_DEGREE);
+    return AMC_OK;
+}
+
+static int step_grid(amc_ctx* c, int dtype, int degree, int64_t n_paths) {
+    int& g = c->grid_cache[dtype][degree];
+    if (g == 0) g = step_grid_size(dtype, degree, c->sm_count);
+    // small path sets: no more blocks than there are pairs of paths to hand out
+    int64_t need = ((n_paths + 1) / 2 + kStepThreads - 1) / kStepThreads;
+    if (need < 1) need = 1;
+    return (int)(need < g ? need : g);
+}
+
+struct EventPool {
+    amc_ctx* c;
+    size_t used = 0;
+    int get(cudaEvent_t* ev) {
+        if (used == c->events.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            c->events.push_back(e);
+        }
+        *ev = c->events[used++];
+        return AMC_OK;
+    }
+};
+
+extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* spec, double* price,
+                             amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out,
+                             amc_lsm_timing* timing, int profile) {
+    if (!c || !p || !price) return fail(AMC_ERR_VALUE, "amc_lsm_price: null argument");
+    if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_lsm_price: path set belongs to another context");
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    if (exercise_step_out && !spec->want_exercise_steps)
+        return fail(AMC_ERR_VALUE, "exercise_step_out needs spec.want_exercise_steps");
+    CU(cudaSetDevice(c->device));
+
+    const int n = p->n_steps, D = spec->degree, dtype = p->dtype;
+    const int64_t P = p->n_local;
+    const double Pg = (double)p->n_global;
+    const bool american = spec->is_american != 0;
+    const bool regress = (american || spec->want_regression) && n >= 1;
+    const bool barrier = !isnan(spec->barrier);
+    const int grid = step_grid(c, dtype, D, P);
+    const double rdt = spec->r * spec->dt;
+
+    // scratch
+    const int64_t ldp = padded_len(P > 0 ? P : 1);
+    if ((rc = ensure(c->U, (size_t)ldp * 8))) return rc;
+    if (spec->want_exercise_steps && (rc = ensure(c->tau, (size_t)ldp * 4))) return rc;
+    if (barrier && (rc = ensure(c->first_hit, (size_t)ldp * 4))) return rc;
+    if ((rc = ensure(c->partials, (size_t)grid * kAccStride * 8))) return rc;
+    if ((rc = ensure(c->sums, kAccStride * 8))) return rc;
+    // diagnostics block: gamma | beta | sv | mean_std | price | rank
+    const size_t nrow = (size_t)(n + 1);
+    const size_t off_gamma = 0, off_beta = nrow * kMaxK, off_sv = 2 * nrow * kMaxK, off_ms = 3 * nrow * kMaxK;
+    const size_t off_price = off_ms + 2 * nrow, off_rank = off_price + 2;    // rank stored as int32 after doubles
+    const size_t diag_bytes = off_rank * 8 + nrow * 4;
+    if ((rc = ensure(c->diag, diag_bytes))) return rc;
+    double* dg = (double*)c->diag.p;
+    int* drank = (int*)(dg + off_rank);
+    CU(cudaMemsetAsync(c->diag.p, 0, diag_bytes, c->stream));
+    CU(cudaMemsetAsync(c->sums.p, 0, kAccStride * 8, c->stream));
+
+    int32_t* tau = spec->want_exercise_steps ? (int32_t*)c->tau.p : nullptr;
+    int32_t* fh = barrier ? (int32_t*)c->first_hit.p : nullptr;
+    if (barrier && P > 0)
+        CU(launch_first_hit(dtype, p->S, p->ld, n + 1, P, spec->barrier, fh, c->stream));
+
+    EventPool pool{c};
+    cudaEvent_t ev_start, ev_stop;
+    if ((rc = pool.get(&ev_start)) || (rc = pool.get(&ev_stop))) return rc;
+    std::vector<cudaEvent_t> step_ev, solve_ev;
+    int n_step = 0, n_solve = 0, n_other = barrier ? 1 : 0;
+    auto bracket = [&](std::vector<cudaEvent_t>& v) -> int {
+        if (!profile) return AMC_OK;
+        cudaEvent_t e;
+        int r2 = pool.get(&e);
+        if (r2) return r2;
+        v.push_back(e);
+        CU(cudaEventRecord(e, c->stream));
+        return AMC_OK;
+    };
+
+    CU(cudaEventRecord(ev_start, c->stream));
+
+    SolveSpec sspec;
+    sspec.degree = D;
+    sspec.basis = spec->basis;
+    sspec.scaling = spec->scaling;
+    sspec.scaling_factor = spec->scaling_factor;
+    sspec.n_paths = Pg;
+
+    auto run_step = [&](int t, int mode, bool moments) -> int {
+        StepArgs a;
+        a.x_dec = (mode != kObserve) ? column(p, t) : nullptr;
+        a.x_reg = moments ? column(p, t - 1) : nullptr;
+        a.U = (double*)c->U.p;
+        a.tau = tau;
+        a.first_hit = fh;
+        a.coef = dg + off_gamma + (size_t)t * kMaxK;
+        a.partials = (double*)c->partials.p;
+        a.n_paths = P;
+        a.t_dec = t;
+        a.mode = mode;
+        a.moments = moments ? 1 : 0;
+        a.is_put = spec->is_put;
+        a.K = spec->K;
+        a.disc_dec = exp(-rdt * (double)t);
+        a.mu_dec = p->mu[t];
+        a.isg_dec = 1.0 / p->sigma[t];
+        a.mu_reg = moments ? p->mu[t - 1] : 0.0;
+        a.isg_reg = moments ? 1.0 / p->sigma[t - 1] : 1.0;
+        int r2;
+        if ((r2 = bracket(step_ev))) return r2;
+        CU(launch_step(dtype, D, grid, a, c->stream));
+        if ((r2 = bracket(step_ev))) return r2;
+        ++n_step;
+        return AMC_OK;
+    };
+
+    auto run_solve = [&](int t_reg, bool final_price) -> int {
+        SolveArgs s;
+        s.partials = (const double*)c->partials.p;
+        s.n_rows = grid;
+        s.sums = (double*)c->sums.p;
+        s.spec = sspec;
+        s.final_price = 0;
+        s.y_scale = final_price ? 1.0 : exp(rdt * (double)t_reg);
+        s.mu_ref = final_price ? 0.0 : p->mu[t_reg];
+        s.sigma_ref = final_price ? 1.0 : 1.0 / (1.0 / p->sigma[t_reg]);   // the scale the kernels effectively used
+        const size_t row = final_price ? 0 : (size_t)t_reg;
+        s.gamma = dg + off_gamma + row * kMaxK;
+        s.beta = dg + off_beta + row * kMaxK;
+        s.sv = dg + off_sv + row * kMaxK;
+        s.mean_std = dg + off_ms + row * 2;
+        s.rank = drank + row;
+        s.price = dg + off_price;
+        int r2;
+        if ((r2 = bracket(solve_ev))) return r2;
+        if (c->world == 1) {
+            s.do_reduce = 1;
+            s.do_solve = final_price ? 0 : 1;
+            s.final_price = final_price ? 1 : 0;
+            CU(launch_solve(s, c->stream));
+            ++n_solve;
+        } else {
+            s.do_reduce = 1; s.do_solve = 0;
+            CU(launch_solve(s, c->stream));
+            NC(g_nccl.AllReduce(c->sums.p, c->sums.p, (size_t)(3 * D + 1), ncclFloat64, ncclSum, c->comm, c->stream));
+            s.do_reduce = 0;
+            s.do_solve = final_price ? 0 : 1;
+            s.final_price = final_price ? 1 : 0;
+            CU(launch_solve(s, c->stream));
+            n_solve += 2;
+            ++n_other;
+        }
+        if ((r2 = bracket(solve_ev))) return r2;
+        return AMC_OK;
+    };
+
+    if (!regress) {
+        // no early exercise and nobody wants continuation values: the price is the discounted mean payoff
+        if ((rc = run_step(n, kMaturity, false))) return rc;
+        if ((rc = run_solve(0, true))) return rc;
+    } else {
+        for (int t = n; t >= 0; --t) {
+            const int mode = (t == n) ? kMaturity : (american ? kDecide : kObserve);
+            if ((rc = run_step(t, mode, t > 0))) return rc;
+            if ((rc = run_solve(t - 1, t == 0))) return rc;
+        }
+    }
+    CU(cudaEventRecord(ev_stop, c->stream));
+
+    double price_h[2] = {0.0, 0.0};
+    CU(cudaMemcpyAsync(price_h, dg + off_price, 8, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> diag_h;
+    std::vector<int> rank_h;
+    if (steps) {
+        diag_h.resize(off_price);
+        rank_h.resize(nrow);
+        CU(cudaMemcpyAsync(diag_h.data(), dg, off_price * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(rank_h.data(), drank, nrow * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (exercise_step_out && P > 0)
+        CU(cudaMemcpyAsync(exercise_step_out, tau, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cashflow0_out && P > 0)
+        CU(cudaMemcpyAsync(cashflow0_out, c->U.p, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *price = price_h[0];
+
+    if (steps) {
+        if (steps->gamma) memcpy(steps->gamma, diag_h.data() + off_gamma, nrow * kMaxK * 8);
+        if (steps->beta) memcpy(steps->beta, diag_h.data() + off_beta, nrow * kMaxK * 8);
+        if (steps->sv) memcpy(steps->sv, diag_h.data() + off_sv, nrow * kMaxK * 8);
+        for (size_t t = 0; t < nrow; ++t) {
+            if (steps->mean_x) steps->mean_x[t] = diag_h[off_ms + 2 * t];
+            if (steps->std_x) steps->std_x[t] = diag_h[off_ms + 2 * t + 1];
+            if (steps->rank) steps->rank[t] = rank_h[t];
+        }
+    }
+    if (timing) {
+        memset(timing, 0, sizeof(*timing));
+        CU(cudaEventElapsedTime(&timing->total_ms, ev_start, ev_stop));
+        for (size_t i = 0; i + 1 < step_ev.size(); i += 2) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, step_ev[i], step_ev[i + 1]));
+            timing->step_kernel_ms += ms;
+        }
+        for (size_t i = 0; i + 1 < solve_ev.size(); i += 2) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, solve_ev[i], solve_ev[i + 1]));
+            timing->solve_kernel_ms += ms;
+        }
+        timing->step_launches = n_step;
+        timing->solve_launches = n_solve;
+        timing->other_launches = n_other;
+    }
+    return AMC_OK;
+}
+
+extern "C" int amc_continuation(amc_ctx* c, const amc_paths* p, int t, const double* gamma, int degree, double* out) {
+    if (!c || !p || !gamma || !out) return fail(AMC_ERR_VALUE, "amc_continuation: null argument");
+    if (t < 0 || t > p->n_steps) return fail(AMC_ERR_VALUE, "step %d out of range", t);
+    if (degree < 0 || degree > AMC_MAX_DEGREE) return fail(AMC_ERR_VALUE, "degree %d outside 0..%d", degree, AMC_MAX_DEGREE);
+    if (p->n_local == 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure(c->misc, (size_t)p->n_local * 8 + kMaxK * 8);
+    if (rc) return rc;
+    double* out_dev = (double*)c->misc.p;
+    double* gam_dev = out_dev + p->n_local;
+    CU(cudaMemcpyAsync(gam_dev, gamma, (size_t)(degree + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_continuation(p->dtype, column(p, t), p->n_local, gam_dev, degree, p->mu[t], 1.0 / p->sigma[t], 1, out_dev,
+                           c->stream));
+    CU(cudaMemcpyAsync(out, out_dev, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int amc_intrinsic_value(amc_ctx* c, const double* S, int64_t n, double K, int is_put, double* out) {
+    if (!c || (n > 0 && (!S || !out))) return fail(AMC_ERR_VALUE, "amc_intrinsic_value: null argument");
+    if (n <= 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure(c->misc, (size_t)n * 16);
+    if (rc) return rc;
+    double* in_dev = (double*)c->misc.p;
+    double* out_dev = in_dev + n;
+    CU(cudaMemcpyAsync(in_dev, S, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_intrinsic(in_dev, n, K, is_put, out_dev, c->stream));
+    CU(cudaMemcpyAsync(out, out_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_basis_matrix(amc_ctx* c, const double* X, int64_t n, int basis, int degree, double* out) {
+    if (!c || (n > 0 && (!X || !out))) return fail(AMC_ERR_VALUE, "amc_basis_matrix: null argument");
+    if (basis < 0 || basis > AMC_BASIS_LAGUERRE)
+        return fail(AMC_ERR_VALUE, "Unknown basis type id %d. Use 'Power', 'Chebyshev', or 'Legendre'.", basis);
+    if (degree < 0 || degree > AMC_MAX_DEGREE) return fail(AMC_ERR_VALUE, "degree %d outside 0..%d", degree, AMC_MAX_DEGREE);
+    if (n <= 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t k = (size_t)degree + 1;
+    int rc = ensure(c->misc, (size_t)n * 8 * (k + 1));
+    if (rc) return rc;
+    double* in_dev = (double*)c->misc.p;
+    double* out_dev = in_dev + n;
+    CU(cudaMemcpyAsync(in_dev, X, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_basis_matrix(in_dev, n, basis, degree, out_dev, c->stream));
+    CU(cudaMemcpyAsync(out, out_dev, (size_t)n * k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, int64_t n, int basis, int degree,
+                                  int scaling, double scaling_factor, double* fitted, double* beta, int* rank) {
+    if (!c || (n > 0 && (!X || !Y || !fitted))) return fail(AMC_ERR_VALUE, "amc_regression_fit: null argument");
+    amc_lsm_spec sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.basis = basis;
+    sp.degree = degree;
+    int rc = check_spec(&sp);
+    if (rc) return rc;
+    if (n <= 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    // a one-column path set holding X; Y plays the role of the per-path state
+    amc_paths* px = nullptr;
+    if ((rc = paths_alloc(c, 0, n, n, AMC_F64, &px))) return rc;
+    auto cleanup = [&](int code) { amc_paths_free(px); return code; };
+    cudaError_t e = cudaMemcpyAsync(px->S, X, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "H2D X: %s", cudaGetErrorString(e)));
+    const int world_saved = c->world;
+    c->world = 1;                                   // statistics of THIS array only
+    rc = measured_maps(c, px);
+    c->world = world_saved;
+    if (rc) return cleanup(rc);
+    const int grid = step_grid(c, AMC_F64, degree, n);
+    const int64_t ldp = padded_len(n);
+    if ((rc = ensure(c->U, (size_t)ldp * 8)) || (rc = ensure(c->partials, (size_t)grid * kAccStride * 8)) ||
+        (rc = ensure(c->sums, kAccStride * 8)) || (rc = ensure(c->diag, (4 * kMaxK + 8) * 8)))
+        return cleanup(rc);
+    e = cudaMemcpyAsync(c->U.p, Y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "H2D Y: %s", cudaGetErrorString(e)));
+    double* dg = (double*)c->diag.p;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x_reg = px->S;
+    a.U = (double*)c->U.p;
+    a.partials = (double*)c->partials.p;
+    a.n_paths = n;
+    a.t_dec = 1;
+    a.mode = kObserve;
+    a.moments = 1;
+    a.mu_reg = px->mu[0];
+    a.isg_reg = 1.0 / px->sigma[0];
+    e = launch_step(AMC_F64, degree, grid, a, c->stream);
+    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "moment kernel: %s", cudaGetErrorString(e)));
+    SolveArgs s;
+    memset(&s, 0, sizeof(s));
+    s.partials = (const double*)c->partials.p;
+    s.n_rows = grid;
+    s.sums = (double*)c->sums.p;
+    s.do_reduce = 1;
+    s.do_solve = 1;
+    s.spec.degree = degree;
+    s.spec.basis = basis;
+    s.spec.scaling = scaling;
+    s.spec.scaling_factor = scaling_factor;
+    s.spec.n_paths = (double)n;
+    s.y_scale = 1.0;
+    s.mu_ref = px->mu[0];
+    s.sigma_ref = 1.0 / a.isg_reg;
+    s.gamma = dg;
+    s.beta = dg + kMaxK;
+    s.sv = dg + 2 * kMaxK;
+    s.mean_std = dg + 3 * kMaxK;
+    s.rank = (int*)(dg + 3 * kMaxK + 2);
+    s.price = dg + 3 * kMaxK + 4;
+    e = launch_solve(s, c->stream);
+    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "solve kernel: %s", cudaGetErrorString(e)));
+    if ((rc = ensure(c->misc, (size_t)n * 8))) return cleanup(rc);
+    e = launch_continuation(AMC_F64, px->S, n, dg, degree, px->mu[0], a.isg_reg, 0, (double*)c->misc.p, c->stream);
+    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "fit kernel: %s", cudaGetErrorString(e)));
+    double small[3 * kMaxK + 4];
+    cudaMemcpyAsync(fitted, c->misc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(small, dg, sizeof(small), cudaMemcpyDeviceToHost, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "regression fit: %s", cudaGetErrorString(e)));
+    if (beta) memcpy(beta, small + kMaxK, (size_t)(degree + 1) * 8);
+    if (rank) memcpy(rank, small + 3 * kMaxK + 2, 4);
+    return cleanup(AMC_OK);
+}
+
+extern "C" int amc_barrier_hit_matrix(amc_ctx* c, const amc_paths* p, double barrier, uint8_t* out) {
+    if (!c || !p || !out) return fail(AMC_ERR_VALUE, "amc_barrier_hit_matrix: null argument");
+    if (p->n_local == 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t total = (size_t)p->n_local * (size_t)(p->n_steps + 1);
+    if (isnan(barrier)) {                      // amc.py:175: no barrier -> all True
+        memset(out, 1, total);
+        return AMC_OK;
+    }
+    int rc = ensure(c->first_hit, (size_t)padded_len(p->n_local) * 4);
+    if (rc) return rc;
+    if ((rc = ensure(c->misc, total))) return rc;
+    CU(launch_first_hit(p->dtype, p->S, p->ld, p->n_steps + 1, p->n_local, barrier, (int32_t*)c->first_hit.p, c->stream));
+    CU(launch_hit_matrix((const int32_t*)c->first_hit.p, p->n_steps + 1, p->n_local, (uint8_t*)c->misc.p, c->stream));
+    CU(cudaMemcpyAsync(out, c->misc.p, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}

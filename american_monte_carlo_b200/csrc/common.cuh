@@ -1,0 +1,80 @@
+// Shared device helpers: streaming vector loads/stores, deterministic block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amc {
+
+constexpr int kWarp = 32;
+
+// ---- 128-bit streaming accesses ------------------------------------------------------------------------
+// Path columns and the per-path state are touched once per launch: bypass L1 allocation so the 126 MB L2
+// (which may still hold the column from the previous step's launch) is the only cache level involved.
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int2 ld_stream(const int2* p) {
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+// state arrays are read AND written by the same launch: plain (coherent) load, no L1 allocation
+__device__ __forceinline__ double2 ld_state(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(double2* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream(int2* p, int2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// ---- reductions ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction of NACC per-thread accumulators into out[0..NACC) (global memory, one row
+// per block).  Order is fixed by (lane, warp) -> bitwise reproducible for a given launch geometry.
+template <int NACC, int THREADS>
+__device__ __forceinline__ void block_reduce_store(const double (&acc)[NACC], double* smem /*[THREADS/32][NACC]*/,
+                                                   double* out_row) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = warp_sum(acc[a]);
+        if (lane == 0) smem[warp * NACC + a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) v += smem[w * NACC + threadIdx.x];
+        out_row[threadIdx.x] = v;
+    }
+}
+
+}  // namespace amc

@@ -1,0 +1,88 @@
+// Host-callable launchers of the device kernels (implemented in pathgen.cu / lsm_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lsm_solve.h"
+
+namespace amc {
+
+constexpr int kAccStride = 32;     // doubles per partial-sum row: 2d moment sums + (d+1) cross sums <= 31
+constexpr int kStepThreads = 256;
+constexpr int kPadElems = 32;      // columns are padded to a multiple of 32 elements (128 B for f32)
+
+inline int64_t padded_len(int64_t n) { return (n + kPadElems - 1) / kPadElems * kPadElems; }
+
+enum StepMode {
+    kMaturity = 0,   // t = n: cashflow = payoff where knocked in (amc.py:147-149)
+    kDecide = 1,     // t < n, American: exercise where payoff > max(fit, 0) (amc.py:154-162, 90-94)
+    kObserve = 2     // t < n, no early exercise: the state is only read (regression target for t-1)
+};
+
+struct StepArgs {
+    const void* x_dec;         // column t_dec   (null when nothing is decided: kObserve)
+    const void* x_reg;         // column t_dec-1 (null when moments == 0)
+    double* U;                 // per-path cashflow discounted to time 0
+    int32_t* tau;              // optional exercise step per path
+    const int32_t* first_hit;  // optional first knock-in step per path (barrier)
+    const double* coef;        // gamma of step t_dec (device, kMaxK doubles); unused at maturity
+    double* partials;          // [grid][kAccStride]
+    int64_t n_paths;           // local
+    int t_dec;
+    int mode;
+    int moments;               // 1: moment sums of column t_dec-1; 0: only sum(U) (last launch -> price)
+    int is_put;
+    double K, disc_dec;        // strike, exp(-r dt t_dec)
+    double mu_dec, isg_dec;    // affine map of column t_dec:   z = (x - mu) * isg
+    double mu_reg, isg_reg;    // affine map of column t_dec-1
+};
+
+struct SolveArgs {
+    const double* partials;    // [n_rows][kAccStride] (null: skip the reduction, sums already hold totals)
+    int n_rows;
+    double* sums;              // [kAccStride] reduced (and, multi-GPU, all-reduced) sums
+    int do_reduce, do_solve, final_price;
+    SolveSpec spec;
+    double y_scale;            // exp(r dt t): brings the time-0 cashflows to time t
+    double mu_ref, sigma_ref;  // affine map of the regressed column
+    // outputs (device)
+    double* gamma;             // [kMaxK]
+    double* beta;              // [kMaxK]
+    double* sv;                // [kMaxK]
+    double* mean_std;          // [2]
+    int* rank;                 // [1]
+    double* price;             // [1] (final_price)
+};
+
+int step_grid_size(int dtype, int degree, int sm_count);
+cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s);
+cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s);
+cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const double* gamma_dev, int degree, double mu,
+                                double isg, int clamp, double* out_dev, cudaStream_t s);
+cudaError_t launch_intrinsic(const double* S_dev, int64_t n, double K, int is_put, double* out_dev, cudaStream_t s);
+cudaError_t launch_basis_matrix(const double* X_dev, int64_t n, int basis, int degree, double* out_dev,
+                                cudaStream_t s);
+
+// pathgen.cu
+struct GbmParams {
+    double S0, drift, vol;     // per-step log drift (r - sigma^2/2) dt and vol sigma sqrt(dt)
+};
+cudaError_t launch_generate_philox(int dtype, void* S, int64_t ld, int n_steps, int64_t n_local, int64_t path_offset,
+                                   GbmParams g, uint64_t seed, int sm_count, cudaStream_t s);
+cudaError_t launch_from_normals(int dtype, const double* Z_dev, void* S, int64_t ld, int n_steps, int64_t n_local,
+                                GbmParams g, cudaStream_t s);
+cudaError_t launch_transpose_in(int dtype, const double* S_rowmajor_dev, void* S, int64_t ld, int n_cols,
+                                int64_t n_local, cudaStream_t s);
+cudaError_t launch_gather_rows(int dtype, const void* S, int64_t ld, int n_cols, int64_t p0, int64_t p1,
+                               double* out_dev, cudaStream_t s);
+cudaError_t launch_column_to_f64(int dtype, const void* col, int64_t n, double* out_dev, cudaStream_t s);
+// shifted one-pass column statistics: partial[(col * n_chunks + chunk) * 2 + {0,1}] = sum(x - c), sum((x - c)^2)
+// with c = first element of the column
+cudaError_t launch_column_stats(int dtype, const void* S, int64_t ld, int n_cols, int64_t n_local, int n_chunks,
+                                double* partial_dev, double* shift_dev, cudaStream_t s);
+cudaError_t launch_first_hit(int dtype, const void* S, int64_t ld, int n_cols, int64_t n_local, double barrier,
+                             int32_t* first_hit_dev, cudaStream_t s);
+cudaError_t launch_hit_matrix(const int32_t* first_hit_dev, int n_cols, int64_t n_local, uint8_t* out_dev,
+                              cudaStream_t s);
+
+}  // namespace amc

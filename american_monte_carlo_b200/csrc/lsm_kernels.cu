@@ -1,0 +1,345 @@
+// LSM backward-induction kernels for sm_100a.
+//
+//  lsm_step_kernel<XT, D>  one launch per time step t: fused
+//        (1) exercise decision at step t for every path  (amc.py:147-149 at maturity, :154-162/:90-94 below it)
+//        (2) moment sums of the regression of step t-1   (the O(P) part of amc.py:110-128)
+//      Reads column t, column t-1 and the per-path state once, writes the state once:
+//      2*b_S + 16 algorithmic bytes per path-step -- an HBM-streaming kernel (FP64 FMA work ~30-90 flop per
+//      32-48 B, far below the tensor-core regime; no dense contraction exists at k <= 11).
+//  lsm_solve_kernel        single block between two step launches: fixed-order reduction of the per-block
+//      partial sums, then one thread runs lsm_solve.h (Cholesky + change of basis + Jacobi SVD + numpy's
+//      rank rule) and leaves the continuation polynomial in device memory for the next step launch.
+//
+// State: U[p] = cashflow of path p discounted to time 0 (= cashflows * exp(-r dt exercise_times) of
+// amc.py:128,196, which the reference recomputes at every step).  The regression target at step t is
+// Y = U * exp(r dt t); the scalar factor is applied to the reduced sums, not per path.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace amc {
+
+template <typename XT> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <typename XT>
+__device__ __forceinline__ void load_pair(const XT* col, int64_t unit, double& a, double& b) {
+    typename Vec2<XT>::type v = __ldg(reinterpret_cast<const typename Vec2<XT>::type*>(col) + unit);
+    a = (double)v.x;
+    b = (double)v.y;
+}
+
+// power sums of one path: acc[m-1] += z^m (m = 1..2D), acc[2D+m] += z^m * y (m = 0..D)
+template <int D>
+__device__ __forceinline__ void accumulate_moments(double z, double y, double (&acc)[3 * D + 1]) {
+    acc[2 * D] += y;
+    double p = 1.0;
+#pragma unroll
+    for (int m = 1; m <= 2 * D; ++m) {
+        p *= z;
+        acc[m - 1] += p;
+        if (m <= D) acc[2 * D + m] = fma(p, y, acc[2 * D + m]);
+    }
+}
+
+template <int D>
+__device__ __forceinline__ double horner(const double (&gam)[D + 1], double z) {
+    double f = gam[D];
+#pragma unroll
+    for (int m = D - 1; m >= 0; --m) f = fma(f, z, gam[m]);
+    return f;
+}
+
+// One path: decision at t_dec, then moments at t_dec-1.  All flags are launch-uniform.
+template <int D>
+__device__ __forceinline__ void path_step(const StepArgs& a, const double (&gam)[D + 1], double xd, double xr,
+                                          double& u, int& tau, int fh, double (&acc)[3 * D + 1]) {
+    if (a.mode != kObserve) {
+        const double iv = a.is_put ? (a.K - xd) : (xd - a.K);
+        const bool in = (fh <= a.t_dec);
+        if (a.mode == kMaturity) {
+            // cashflows[hit] = max(payoff, 0), exercise_times[hit] = n; everything else stays 0 / n
+            u = (in && iv > 0.0) ? iv * a.disc_dec : 0.0;
+            tau = a.t_dec;
+        } else {
+            const double zd = (xd - a.mu_dec) * a.isg_dec;
+            const double fit = horner<D>(gam, zd);
+            // candidates: knocked in AND in the money; exercise iff payoff > max(fit, 0)  (strict)
+            if (in && iv > 0.0 && iv > fit) {
+                u = iv * a.disc_dec;
+                tau = a.t_dec;
+            }
+        }
+    }
+    if (a.moments) {
+        const double zr = (xr - a.mu_reg) * a.isg_reg;
+        accumulate_moments<D>(zr, u, acc);
+    } else {
+        acc[2 * D] += u;
+    }
+}
+
+template <typename XT, int D>
+__global__ void __launch_bounds__(kStepThreads) lsm_step_kernel(const StepArgs a) {
+    constexpr int NACC = 3 * D + 1;
+    __shared__ double red[(kStepThreads / 32) * NACC];
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    double gam[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) gam[i] = (a.mode == kDecide) ? a.coef[i] : 0.0;
+
+    const XT* xdec = static_cast<const XT*>(a.x_dec);
+    const XT* xreg = static_cast<const XT*>(a.x_reg);
+    const bool need_dec = (a.mode != kObserve);
+    const bool need_u_in = (a.mode != kMaturity);
+    const bool write_u = (a.mode != kObserve);
+
+    const int64_t n_units = a.n_paths >> 1;                       // full pairs
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+    double2* U2 = reinterpret_cast<double2*>(a.U);
+    int2* T2 = reinterpret_cast<int2*>(a.tau);
+    const int2* F2 = reinterpret_cast<const int2*>(a.first_hit);
+
+    // two independent pairs per iteration: all loads are issued before the arithmetic
+    int64_t q = tid;
+    for (; q + stride < n_units; q += 2 * stride) {
+        const int64_t q1 = q + stride;
+        double xd0 = 0, xd1 = 0, xd2 = 0, xd3 = 0, xr0 = 0, xr1 = 0, xr2 = 0, xr3 = 0;
+        double2 u0 = make_double2(0.0, 0.0), u1 = make_double2(0.0, 0.0);
+        int2 f0 = make_int2(0, 0), f1 = make_int2(0, 0), t0 = make_int2(0, 0), t1 = make_int2(0, 0);
+        if (need_dec) { load_pair<XT>(xdec, q, xd0, xd1); load_pair<XT>(xdec, q1, xd2, xd3); }
+        if (a.moments) { load_pair<XT>(xreg, q, xr0, xr1); load_pair<XT>(xreg, q1, xr2, xr3); }
+        if (need_u_in) { u0 = U2[q]; u1 = U2[q1]; }
+        if (F2) { f0 = __ldg(F2 + q); f1 = __ldg(F2 + q1); }
+        if (T2 && need_u_in) { t0 = T2[q]; t1 = T2[q1]; }
+        path_step<D>(a, gam, xd0, xr0, u0.x, t0.x, f0.x, acc);
+        path_step<D>(a, gam, xd1, xr1, u0.y, t0.y, f0.y, acc);
+        path_step<D>(a, gam, xd2, xr2, u1.x, t1.x, f1.x, acc);
+        path_step<D>(a, gam, xd3, xr3, u1.y, t1.y, f1.y, acc);
+        if (write_u) {
+            U2[q] = u0; U2[q1] = u1;
+            if (T2) { T2[q] = t0; T2[q1] = t1; }
+        }
+    }
+    for (; q < n_units; q += stride) {
+        double xd0 = 0, xd1 = 0, xr0 = 0, xr1 = 0;
+        double2 u0 = make_double2(0.0, 0.0);
+        int2 f0 = make_int2(0, 0), t0 = make_int2(0, 0);
+        if (need_dec) load_pair<XT>(xdec, q, xd0, xd1);
+        if (a.moments) load_pair<XT>(xreg, q, xr0, xr1);
+        if (need_u_in) u0 = U2[q];
+        if (F2) f0 = __ldg(F2 + q);
+        if (T2 && need_u_in) t0 = T2[q];
+        path_step<D>(a, gam, xd0, xr0, u0.x, t0.x, f0.x, acc);
+        path_step<D>(a, gam, xd1, xr1, u0.y, t0.y, f0.y, acc);
+        if (write_u) {
+            U2[q] = u0;
+            if (T2) T2[q] = t0;
+        }
+    }
+    // odd path count: the last path is handled by the thread that would own the next unit
+    if ((a.n_paths & 1) && tid == (n_units % stride)) {
+        const int64_t p = a.n_paths - 1;
+        double xd = need_dec ? (double)xdec[p] : 0.0;
+        double xr = a.moments ? (double)xreg[p] : 0.0;
+        double u = need_u_in ? a.U[p] : 0.0;
+        int fh = a.first_hit ? a.first_hit[p] : 0;
+        int tau = (a.tau && need_u_in) ? a.tau[p] : 0;
+        path_step<D>(a, gam, xd, xr, u, tau, fh, acc);
+        if (write_u) {
+            a.U[p] = u;
+            if (a.tau) a.tau[p] = tau;
+        }
+    }
+    block_reduce_store<NACC, kStepThreads>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Solve kernel: <<<1, 128>>>.
+//   phase 1 (do_reduce): sums[a] = sum over rows of partials[row][a], fixed order (lane-strided, then a
+//                        shuffle tree) -> bitwise reproducible, no floating-point atomics anywhere.
+//   phase 2 (do_solve):  thread 0 runs the k x k solve and stores gamma / diagnostics.
+//   final_price:         price = sum(U) / P.
+// Multi-GPU: phase 1, then an NCCL all-reduce of `sums`, then phase 2 as a second launch.
+__global__ void __launch_bounds__(128) lsm_solve_kernel(const SolveArgs a) {
+    const int d = a.spec.degree;
+    const int nacc = 3 * d + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.do_reduce) {
+        for (int acc = warp; acc < nacc; acc += 4) {
+            double v = 0.0;
+            for (int row = lane; row < a.n_rows; row += 32) v += a.partials[(int64_t)row * kAccStride + acc];
+            v = warp_sum(v);
+            if (lane == 0) a.sums[acc] = v;
+        }
+        __syncthreads();
+        __threadfence();
+    }
+    if (threadIdx.x != 0) return;
+    if (a.final_price) {
+        a.price[0] = a.sums[2 * d] / a.spec.n_paths;
+        return;
+    }
+    if (!a.do_solve) return;
+    double h[2 * kMaxK], g[kMaxK];
+    h[0] = a.spec.n_paths;
+    for (int m = 1; m <= 2 * d; ++m) h[m] = a.sums[m - 1];
+    for (int m = 0; m <= d; ++m) g[m] = a.sums[2 * d + m];
+    SolveResult res;
+    lsm_solve(a.spec, h, g, a.y_scale, a.mu_ref, a.sigma_ref, &res);
+    for (int i = 0; i < kMaxK; ++i) {
+        a.gamma[i] = res.gamma[i];
+        if (a.beta) a.beta[i] = res.beta[i];
+        if (a.sv) a.sv[i] = res.sv[i];
+    }
+    if (a.mean_std) { a.mean_std[0] = res.mean_x; a.mean_std[1] = res.std_x; }
+    if (a.rank) a.rank[0] = res.rank;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Continuation value of every path at one step from a stored polynomial (lazy replacement for the two [P]
+// copies the reference appends per step, amc.py:164): out = clamp ? max(fit, 0) : fit.
+template <typename XT>
+__global__ void continuation_kernel(const XT* __restrict__ x, int64_t n, const double* __restrict__ gamma, int degree,
+                                    double mu, double isg, int clamp, double* __restrict__ out) {
+    double gam[kMaxK];
+    for (int i = 0; i <= degree; ++i) gam[i] = gamma[i];
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const double z = ((double)x[p] - mu) * isg;
+        double f = gam[degree];
+        for (int m = degree - 1; m >= 0; --m) f = fma(f, z, gam[m]);
+        // np.maximum propagates NaN; fmax would drop it
+        out[p] = clamp ? ((f > 0.0 || f != f) ? f : 0.0) : f;
+    }
+}
+
+__global__ void intrinsic_kernel(const double* __restrict__ S, int64_t n, double K, int is_put, double* __restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const double v = is_put ? (K - S[p]) : (S[p] - K);
+        out[p] = (v > 0.0 || v != v) ? v : 0.0;     // np.maximum(v, 0)
+    }
+}
+
+// get_basis_polynomials (amc.py:98-106): out[p][j] = phi_j(x_p), three-term recurrences in x.
+__global__ void basis_matrix_kernel(const double* __restrict__ X, int64_t n, int basis, int degree,
+                                    double* __restrict__ out) {
+    const int k = degree + 1;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const double x = X[p];
+        double* row = out + p * k;
+        double pm2 = 0.0, pm1 = 1.0;
+        row[0] = 1.0;
+        for (int j = 1; j < k; ++j) {
+            double v;
+            switch (basis) {
+                case kChebyshev: v = (j == 1) ? x : 2.0 * x * pm1 - pm2; break;
+                case kLegendre: v = ((2.0 * j - 1.0) * x * pm1 - (j - 1.0) * pm2) / (double)j; break;
+                case kLaguerre: v = ((2.0 * j - 1.0 - x) * pm1 - (j - 1.0) * pm2) / (double)j; break;
+                default: v = pm1 * x;
+            }
+            row[j] = v;
+            pm2 = pm1;
+            pm1 = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+template <typename XT, int D>
+static cudaError_t launch_step_t(int grid, const StepArgs& a, cudaStream_t s) {
+    lsm_step_kernel<XT, D><<<grid, kStepThreads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename XT>
+static cudaError_t launch_step_d(int degree, int grid, const StepArgs& a, cudaStream_t s) {
+    switch (degree) {
+        case 0: return launch_step_t<XT, 0>(grid, a, s);
+        case 1: return launch_step_t<XT, 1>(grid, a, s);
+        case 2: return launch_step_t<XT, 2>(grid, a, s);
+        case 3: return launch_step_t<XT, 3>(grid, a, s);
+        case 4: return launch_step_t<XT, 4>(grid, a, s);
+        case 5: return launch_step_t<XT, 5>(grid, a, s);
+        case 6: return launch_step_t<XT, 6>(grid, a, s);
+        case 7: return launch_step_t<XT, 7>(grid, a, s);
+        case 8: return launch_step_t<XT, 8>(grid, a, s);
+        case 9: return launch_step_t<XT, 9>(grid, a, s);
+        case 10: return launch_step_t<XT, 10>(grid, a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s) {
+    return dtype == 1 ? launch_step_d<float>(degree, grid, a, s) : launch_step_d<double>(degree, grid, a, s);
+}
+
+template <typename XT, int D>
+static int occupancy_blocks() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lsm_step_kernel<XT, D>, kStepThreads, 0);
+    return nb;
+}
+
+template <typename XT>
+static int occupancy_d(int degree) {
+    switch (degree) {
+        case 0: return occupancy_blocks<XT, 0>();
+        case 1: return occupancy_blocks<XT, 1>();
+        case 2: return occupancy_blocks<XT, 2>();
+        case 3: return occupancy_blocks<XT, 3>();
+        case 4: return occupancy_blocks<XT, 4>();
+        case 5: return occupancy_blocks<XT, 5>();
+        case 6: return occupancy_blocks<XT, 6>();
+        case 7: return occupancy_blocks<XT, 7>();
+        case 8: return occupancy_blocks<XT, 8>();
+        case 9: return occupancy_blocks<XT, 9>();
+        case 10: return occupancy_blocks<XT, 10>();
+    }
+    return 1;
+}
+
+// grid = SM count x resident blocks per SM: every block is co-resident, the grid-stride loop balances.
+int step_grid_size(int dtype, int degree, int sm_count) {
+    int nb = dtype == 1 ? occupancy_d<float>(degree) : occupancy_d<double>(degree);
+    if (nb < 1) nb = 1;
+    return sm_count * nb;
+}
+
+cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s) {
+    lsm_solve_kernel<<<1, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+static inline int blocks_for(int64_t n, int threads, int cap) {
+    int64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    return (int)(b > cap ? cap : b);
+}
+
+cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const double* gamma_dev, int degree, double mu,
+                                double isg, int clamp, double* out_dev, cudaStream_t s) {
+    const int grid = blocks_for(n, 256, 148 * 8);
+    if (dtype == 1)
+        continuation_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, gamma_dev, degree, mu, isg, clamp, out_dev);
+    else
+        continuation_kernel<double><<<grid, 256, 0, s>>>((const double*)x, n, gamma_dev, degree, mu, isg, clamp, out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_intrinsic(const double* S_dev, int64_t n, double K, int is_put, double* out_dev, cudaStream_t s) {
+    intrinsic_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, s>>>(S_dev, n, K, is_put, out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_basis_matrix(const double* X_dev, int64_t n, int basis, int degree, double* out_dev,
+                                cudaStream_t s) {
+    basis_matrix_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, s>>>(X_dev, n, basis, degree, out_dev);
+    return cudaGetLastError();
+}
+
+}  // namespace amc

@@ -17,3 +17,10 @@ extern "C" int amc_test_lsm_solve(int degree, int basis, int scaling, double sca
     info[0] = res.rank; info[1] = res.k_internal; info[2] = res.sweeps;
     return 0;
 }
+
+#include "../../american_monte_carlo_b200/csrc/philox.cuh"
+extern "C" void amc_test_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                uint32_t* out) {
+    amc::Philox4 r = amc::philox4x32_10(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+}

@@ -1,0 +1,69 @@
+"""CPU tier: libamc.so builds for sm_100a, loads without a GPU, exports every symbol include/amc.h declares,
+and fails loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "amc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(amc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_documented_entry_points():
+    syms = declared_symbols()
+    for must in ["amc_ctx_create", "amc_paths_generate", "amc_paths_from_normals", "amc_paths_from_host",
+                 "amc_lsm_price", "amc_continuation", "amc_comm_init", "amc_intrinsic_value", "amc_regression_fit"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(libamc_path):
+    lib = ctypes.CDLL(libamc_path)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_every_declared_symbol(libamc_path):
+    from american_monte_carlo_b200 import _native
+    assert sorted(_native.PROTOTYPES) == declared_symbols()
+    _native.lib()
+
+
+def test_library_is_sm100a_and_has_no_cpu_path(libamc_path):
+    out = subprocess.run(["cuobjdump", "--list-elf", libamc_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the failure mode below only exists on a CPU box")
+    import american_monte_carlo_b200 as pkg
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pkg.Context(0)
+    import numpy as np
+    pkg.set_default_context(None)
+    with pytest.raises(RuntimeError):
+        pkg.intrinsic_value(np.array([90.0, 100.0]), 100.0, "Put")
+
+
+def test_unknown_basis_is_a_value_error_before_any_device_work():
+    import american_monte_carlo_b200 as pkg
+    import numpy as np
+    with pytest.raises(ValueError, match="Unknown basis type 'Hermite'"):
+        pkg.get_basis_polynomials(np.ones(3), "Hermite", 2)
+    with pytest.raises(TypeError, match="unexpected keyword argument 'bogus'"):
+        pkg.lsmc_option_pricing(np.ones((4, 3)), 1.0, 0.0, 0.1, "Put", bogus=1)
+
+
+def test_shard_range_partitions_the_path_axis():
+    from american_monte_carlo_b200 import shard_range
+    for P, W in [(100_000_000, 8), (10, 3), (7, 8), (0, 2), (1, 1)]:
+        parts = [shard_range(P, W, r) for r in range(W)]
+        assert parts[0][0] == 0 and parts[-1][1] == P
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1

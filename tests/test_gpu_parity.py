@@ -1,0 +1,250 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): identical injected normals -> price within 1e-10 relative in FP64 and NOT ONE
+path exercising at a different step; 1e-5 relative with FP32 path storage; Monte Carlo standard error with the
+independent Philox stream.
+"""
+import numpy as np
+import pytest
+
+from conftest import oracle_case
+from oracle import lsm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["nb_european_put", "nb_american_put", "nb_di70_european_put", "nb_di70_european_put_200x10000",
+         "nb_di70_european_put_unscaled", "ut_Put_European_None", "ut_Call_European_None", "ut_Put_American_None",
+         "ut_Call_American_None", "ut_Put_European_80", "ut_Call_European_80", "ut_Put_American_80",
+         "ut_Call_American_80", "ut_Put_European_60", "ut_Call_European_60", "ut_Put_American_60",
+         "ut_Call_American_60", "c1_power3", "c1_chebyshev3", "c1_legendre3", "c1_call_power3", "c1_di30_power3",
+         "small_power8_unscaled", "small_legendre8_scaled", "small_chebyshev10_unscaled", "small_degree0",
+         "small_degree1_scaled", "deep_itm_exercise_at_0", "tiny_paths_lt_k"]
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def price_args(c):
+    dt = c["T"] / c["n_time_steps"]
+    return (c["K"], c["r"], dt, c["option_type"], c["barrier_level"], c["exercise_type"], c["basis_type"], c["degree"])
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_injected_normals_price_decisions_and_ranks(amc, golden, name):
+    """K1z + sweep on the reference's own normals: paths, price, every exercise decision, every lstsq rank."""
+    c = golden[name]
+    Z, paths, o = oracle_case(c)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    assert dp.shape == paths.shape
+    got_paths = np.asarray(dp)
+    assert np.max(np.abs(got_paths - paths) / paths) < 1e-13         # log-space sum vs cumprod: ~3e-15
+    res = amc.lsm_price(dp, *price_args(c), **c["kwargs"], want_exercise_steps=True, want_cashflows=True,
+                        want_regression=True)
+    n = c["n_time_steps"]
+    flips = int((res.exercise_steps != o.exercise_times).sum())
+    assert flips == 0, f"{flips} paths exercise at a different step"
+    assert rel(res.price, c["price"]) <= 1e-10 or abs(res.price - c["price"]) <= 1e-14
+    assert res.rank[:n].tolist() == c["ranks"]
+    np.testing.assert_allclose(res.cashflow0, o.cashflows * np.exp(-c["r"] * (c["T"] / n) * o.exercise_times),
+                               rtol=1e-12, atol=0)
+    # singular values of the design matrix, where numpy kept them
+    for t, rec in c.get("steps", {}).items():
+        t = int(t)
+        r = rec["rank"]
+        np.testing.assert_allclose(res.sv[t, :r], rec["sv"][:r], rtol=1e-6)
+    dp.free()
+
+
+@pytest.mark.parametrize("name", ["ut_Put_American_80", "c1_power3", "small_power8_unscaled", "nb_american_put",
+                                  "tiny_paths_lt_k"])
+def test_adopted_reference_paths(amc, golden, name):
+    """amc_paths_from_host: the oracle's own [P, n+1] matrix is adopted (measured column maps) -> bit-equal paths."""
+    c = golden[name]
+    _, paths, o = oracle_case(c)
+    dp = amc.paths_from_host(paths)
+    np.testing.assert_array_equal(np.asarray(dp), paths)
+    np.testing.assert_array_equal(dp[:, c["n_time_steps"] // 2], paths[:, c["n_time_steps"] // 2])
+    np.testing.assert_array_equal(dp[1], paths[1])
+    mu, sg = dp.column_maps()
+    np.testing.assert_allclose(mu, paths.mean(axis=0), rtol=1e-12)
+    res = amc.lsm_price(dp, *price_args(c), **c["kwargs"], want_exercise_steps=True)
+    assert int((res.exercise_steps != o.exercise_times).sum()) == 0
+    assert rel(res.price, c["price"]) <= 1e-10
+    # the reference-shaped call on a plain ndarray
+    p2, _ = amc.lsmc_option_pricing(paths, *price_args(c), **c["kwargs"])
+    assert rel(p2, c["price"]) <= 1e-10
+
+
+def test_drop_in_call_sequence_reproduces_notebook_and_unit_test_prices(amc, golden):
+    """np.random.seed + generate_asset_paths + lsmc_option_pricing exactly as unit_test.py:7-12 / the notebook."""
+    for name in ["nb_american_put", "nb_european_put", "nb_di70_european_put_200x10000", "ut_Put_American_None",
+                 "ut_Call_American_60"]:
+        c = golden[name]
+        np.random.seed(c["seed"])
+        paths = amc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], c["n_time_steps"], c["n_paths"])
+        price, cont = amc.lsmc_option_pricing(paths, *price_args(c), **c["kwargs"])
+        assert rel(price, c["price"]) <= 1e-10 or abs(price - c["price"]) < 1e-14
+        assert len(cont) == c["n_time_steps"] + 1
+        if "printed_in_notebook" in c:
+            assert f"{price:.4f}" == c["printed_in_notebook"]
+
+
+@pytest.mark.parametrize("name", ["nb_american_put", "ut_Put_European_80", "c1_power3", "small_legendre8_scaled"])
+def test_lazy_continuation_values(amc, golden, name):
+    c = golden[name]
+    Z, paths, o = oracle_case(c)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    _, cont = amc.lsmc_option_pricing(dp, *price_args(c), **c["kwargs"])
+    n = c["n_time_steps"]
+    for t in sorted({0, 1, n // 2, n - 1, n}):
+        tt, S_t, cv = cont[t]
+        t_o, S_o, cv_o = o.continuation_values[t]
+        assert tt == t_o == t
+        np.testing.assert_allclose(S_t, S_o, rtol=1e-13)
+        scale = max(np.abs(cv_o).max(), 1e-12)
+        assert np.abs(cv - cv_o).max() <= 1e-8 * scale
+    assert (cont[-1][2] == 0).all()
+
+
+def test_fp32_path_storage_within_1e5(amc, golden):
+    c = golden["c1_power3"]
+    Z, paths, o = oracle_case(c)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"], dtype="float32")
+    got = np.asarray(dp)
+    assert np.max(np.abs(got - paths) / paths) < 1e-7
+    np.testing.assert_array_equal(got, paths.astype(np.float32).astype(np.float64))   # f64 arithmetic, one rounding
+    res = amc.lsm_price(dp, *price_args(c), want_exercise_steps=True)
+    assert rel(res.price, c["price"]) <= 1e-5
+    assert (res.exercise_steps != o.exercise_times).mean() < 1e-3
+
+
+def test_philox_paths_statistics_and_price_within_mc_error(amc, golden):
+    c = golden["c1_power3"]
+    P, n = 400_000, c["n_time_steps"]
+    for dtype in ("float64", "float32"):
+        dp = amc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], n, P, rng="philox", seed=1234, dtype=dtype)
+        ST = dp.column(n)
+        logret = np.log(ST / c["S0"])
+        m = (c["r"] - 0.5 * c["sigma"] ** 2) * c["T"]
+        assert abs(logret.mean() - m) < 5 * c["sigma"] / np.sqrt(P)
+        assert abs(logret.std() - c["sigma"]) < 5 * c["sigma"] / np.sqrt(2 * P)
+        # one-step increments are i.i.d. normal: check skewness / kurtosis of a middle step
+        inc = np.log(dp.column(n // 2 + 1) / dp.column(n // 2))
+        zs = (inc - inc.mean()) / inc.std()
+        assert abs((zs ** 3).mean()) < 5 * np.sqrt(6 / P) and abs((zs ** 4).mean() - 3) < 5 * np.sqrt(24 / P)
+        assert (dp.column(0) == c["S0"]).all()
+        res = amc.lsm_price(dp, *price_args(c), want_cashflows=True)
+        se = res.cashflow0.std() / np.sqrt(P)
+        # the golden (100k reference paths) carries its own Monte Carlo error
+        assert abs(res.price - c["price"]) < 4 * se * np.sqrt(1 + P / c["n_paths"])
+        assert abs(res.price - 4.472) < 0.03                                    # Longstaff-Schwartz Table 1: 4.472
+        # determinism and seed sensitivity
+        dp2 = amc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], n, P, rng="philox", seed=1234, dtype=dtype)
+        assert amc.lsm_price(dp2, *price_args(c)).price == res.price
+        dp3 = amc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], n, P, rng="philox", seed=1235, dtype=dtype)
+        assert amc.lsm_price(dp3, *price_args(c)).price != res.price
+
+
+def test_philox_paths_do_not_depend_on_sharding(amc):
+    """Counters are GLOBAL path ids: a shard generated with an offset equals the same rows of the full set."""
+    import ctypes as C
+    from american_monte_carlo_b200 import _native as N
+    ctx = amc.default_context()
+    full = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 13, 1003, rng="philox", seed=7)
+    A = np.asarray(full)
+    for dtype in (N.F64, N.F32):
+        ref = A if dtype == N.F64 else np.asarray(amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 13, 1003,
+                                                                          rng="philox", seed=7, dtype="float32"))
+        h = C.c_void_p()
+        N.check(N.lib().amc_paths_generate(ctx.handle, 36.0, 0.06, 0.2, 1.0, 13, 400, 301, 1003, dtype,
+                                           C.c_uint64(7), C.byref(h)))
+        shard = amc.DevicePaths(ctx, h, 400, 1003, 13, dtype, 301)
+        np.testing.assert_array_equal(np.asarray(shard), ref[301:701])
+
+
+def test_small_array_ops(amc):
+    # unit_test.py:54-62
+    S = np.array([90, 100, 110])
+    np.testing.assert_array_almost_equal(amc.intrinsic_value(S, 100, "Put"), [10, 0, 0])
+    np.testing.assert_array_almost_equal(amc.intrinsic_value(S, 100, "Call"), [0, 0, 10])
+    rng = np.random.default_rng(0)
+    X = 100 * np.exp(0.2 * rng.standard_normal(30000))
+    Y = np.maximum(100 - X, 0) + rng.standard_normal(X.size)
+    for basis, deg, kw in [("Power", 3, {}), ("Chebyshev", 4, {}), ("Legendre", 6, dict(scaling=True)),
+                           ("Chebyshev", 10, dict(scaling=True, scaling_factor=1))]:
+        want = orc.regression_fit(X, Y, basis, deg, **kw)
+        got = amc.regression_estimate(X, Y, basis, deg, **kw)
+        assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max()
+        A = amc.get_basis_polynomials(X[:100] / 100, basis, deg)
+        np.testing.assert_allclose(A, orc.basis_matrix(X[:100] / 100, basis, deg), rtol=1e-11, atol=1e-13)
+    paths = orc.generate_asset_paths(100, 0.01, 0.2, 1.0, 20, 500)
+    for b in (None, 90.0, 10.0, 1e9):
+        np.testing.assert_array_equal(amc.precompute_barrier_hit_matrix(paths, b), orc.knock_in_flags(paths, b))
+
+
+def test_edge_cases(amc):
+    # no early exercise for unknown exercise types (amc.py:154), call for unknown option types (amc.py:86)
+    np.random.seed(3)
+    paths = orc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 10, 2000)
+    dp = amc.paths_from_host(paths)
+    a = amc.lsm_price(dp, 40.0, 0.06, 0.1, "Put", None, "Bermudan", "Power", 3).price
+    b = amc.lsm_price(dp, 40.0, 0.06, 0.1, "Put", None, "European", "Power", 3).price
+    assert a == b and rel(a, orc.lsm_backward(paths, 40.0, 0.06, 0.1, "Put", None, "European", "Power", 3).price) < 1e-13
+    a = amc.lsm_price(dp, 40.0, 0.06, 0.1, "Straddle", None, "American", "Power", 3).price
+    assert rel(a, orc.lsm_backward(paths, 40.0, 0.06, 0.1, "Call", None, "American", "Power", 3).price) < 1e-10
+    # barrier never hit -> 0; barrier always hit -> vanilla
+    assert amc.lsm_price(dp, 40.0, 0.06, 0.1, "Put", 1.0, "American", "Power", 3).price == 0.0
+    v = amc.lsm_price(dp, 40.0, 0.06, 0.1, "Put", None, "American", "Power", 3).price
+    assert amc.lsm_price(dp, 40.0, 0.06, 0.1, "Put", 1e6, "American", "Power", 3).price == v
+    # all out of the money -> 0
+    assert amc.lsm_price(dp, 1.0, 0.06, 0.1, "Put", None, "American", "Power", 3).price == 0.0
+    # sigma = 0: every column is constant, every regression is the rank-1 mean fit
+    flat = orc.paths_from_normals(np.zeros((50, 6)), 36.0, 0.06, 0.0, 1.0)
+    want = orc.lsm_backward(flat, 40.0, 0.06, 1 / 6, "Put", None, "American", "Power", 3).price
+    assert rel(amc.lsmc_option_pricing(flat, 40.0, 0.06, 1 / 6, "Put", None, "American", "Power", 3)[0], want) < 1e-12
+    # odd path counts and a single path
+    for P in (1, 2, 3, 255, 257):
+        np.random.seed(P)
+        pp = orc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 5, P)
+        want = orc.lsm_backward(pp, 40.0, 0.06, 0.2, "Put", None, "American", "Power", 2).price
+        got = amc.lsmc_option_pricing(pp, 40.0, 0.06, 0.2, "Put", None, "American", "Power", 2)[0]
+        assert rel(got, want) < 1e-9 or abs(got - want) < 1e-12, (P, got, want)
+    with pytest.raises(ValueError, match="Unknown basis type"):
+        amc.lsmc_option_pricing(dp, 40.0, 0.06, 0.1, "Put", None, "American", "Hermite", 3)
+    with pytest.raises(ValueError):
+        amc.lsmc_option_pricing(dp, 40.0, 0.06, 0.1, "Put", None, "American", "Power", 11)
+
+
+def test_laguerre_extension_matches_oracle_extension(amc, golden):
+    c = golden["small_legendre8_scaled"]
+    Z, paths, _ = oracle_case(c)
+    dt = c["T"] / c["n_time_steps"]
+    want = orc.lsm_backward(paths, c["K"], c["r"], dt, "Put", None, "American", "Laguerre", 8, scaling=True)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    res = amc.lsm_price(dp, c["K"], c["r"], dt, "Put", None, "American", "Laguerre", 8, scaling=True,
+                        want_exercise_steps=True)
+    assert int((res.exercise_steps != want.exercise_times).sum()) == 0
+    assert rel(res.price, want.price) <= 1e-10
+
+
+@pytest.mark.slow
+def test_config2_10M_paths_fp64_injected_normals(amc, golden):
+    """BASELINE.json configs[1]: 10M x 50, FP64, the reference's own seed-42 normals (drawn here on the host, 4 GB).
+    Size-independent checks: price to 1e-10 of the golden, the histogram of exercise steps identical (a flipped
+    decision moves a path between bins), numpy's rank-3 truncation at t=1 reproduced."""
+    c = golden["c2_power3_10M"]
+    np.random.seed(c["seed"])
+    Z = orc.draw_normals(c["n_paths"], c["n_time_steps"])
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    del Z
+    n = c["n_time_steps"]
+    col = dp.column(n)
+    assert rel(col.sum(), c["path_checksum"][0]) < 1e-13
+    res = amc.lsm_price(dp, *price_args(c), want_exercise_steps=True, want_cashflows=True)
+    assert res.rank[:n].tolist() == c["ranks"] and res.rank[1] == 3
+    hist = np.bincount(res.exercise_steps, minlength=n + 1).tolist()
+    moved = sum(abs(a - b) for a, b in zip(hist, c["exercise_step_hist"]))
+    assert moved == 0, f"exercise-step histogram differs by {moved}"
+    assert int(np.count_nonzero(res.cashflow0)) == c["n_nonzero_cashflows"]
+    assert rel(res.price, c["price"]) <= 1e-10
