@@ -100,7 +100,11 @@ struct amc_ctx {
     DevBuf U, tau, first_hit, partials, sums, diag, stage, misc;
     std::vector<cudaEvent_t> events;
     int grid_cache[2][AMC_MAX_K];
+    // freed path matrices are kept for reuse (all work is ordered on one stream, so a recycled buffer is safe):
+    // a pricing loop then never pays cudaMalloc/cudaFree (both synchronise the device) for multi-GB matrices
+    std::vector<DevBuf> path_pool;
 };
+constexpr size_t kPathPoolMax = 2;
 
 struct amc_paths {
     amc_ctx* ctx = nullptr;
@@ -164,6 +168,8 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
     DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    for (DevBuf& b : c->path_pool)
+        if (b.p) cudaFree(b.p);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -250,10 +256,26 @@ static int paths_alloc(amc_ctx* c, int n_steps, int64_t n_local, int64_t n_globa
     p->dtype = dtype;
     p->ld = padded_len(n_local > 0 ? n_local : 1);
     p->bytes = (size_t)p->ld * (size_t)(n_steps + 1) * elem_size(dtype);
-    cudaError_t e = cudaMalloc(&p->S, p->bytes);
-    if (e != cudaSuccess) {
-        delete p;
-        return fail(AMC_ERR_CUDA, "cudaMalloc of %zu bytes for the path matrix failed: %s", p->bytes, cudaGetErrorString(e));
+    for (size_t i = 0; i < c->path_pool.size(); ++i) {
+        if (c->path_pool[i].cap == p->bytes) {
+            p->S = c->path_pool[i].p;
+            c->path_pool.erase(c->path_pool.begin() + i);
+            break;
+        }
+    }
+    if (!p->S) {
+        cudaError_t e = cudaMalloc(&p->S, p->bytes);
+        if (e != cudaSuccess && !c->path_pool.empty()) {          // give pooled memory back and retry once
+            for (DevBuf& b : c->path_pool) cudaFree(b.p);
+            c->path_pool.clear();
+            cudaGetLastError();
+            e = cudaMalloc(&p->S, p->bytes);
+        }
+        if (e != cudaSuccess) {
+            const size_t bytes = p->bytes;
+            delete p;
+            return fail(AMC_ERR_CUDA, "cudaMalloc of %zu bytes for the path matrix failed: %s", bytes, cudaGetErrorString(e));
+        }
     }
     p->mu.assign(n_steps + 1, 0.0);
     p->sigma.assign(n_steps + 1, 1.0);
@@ -430,9 +452,19 @@ extern "C" int amc_paths_from_host(amc_ctx* c, const double* S, int n_time_steps
 
 extern "C" int amc_paths_free(amc_paths* p) {
     if (!p) return AMC_OK;
-    cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
-    if (p->S) cudaFree(p->S);
+    amc_ctx* c = p->ctx;
+    cudaSetDevice(c->device);
+    if (p->S) {
+        if (c->path_pool.size() < kPathPoolMax) {
+            DevBuf b;
+            b.p = p->S;
+            b.cap = p->bytes;
+            c->path_pool.push_back(b);
+        } else {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(p->S);
+        }
+    }
     delete p;
     return AMC_OK;
 }

@@ -47,12 +47,13 @@ def test_injected_normals_price_decisions_and_ranks(amc, golden, name):
     assert rel(res.price, c["price"]) <= 1e-10 or abs(res.price - c["price"]) <= 1e-14
     assert res.rank[:n].tolist() == c["ranks"]
     np.testing.assert_allclose(res.cashflow0, o.cashflows * np.exp(-c["r"] * (c["T"] / n) * o.exercise_times),
-                               rtol=1e-12, atol=0)
+                               rtol=1e-12, atol=1e-12 * c["K"])       # K - S cancels: paths agree to ~3e-15 * S
     # singular values of the design matrix, where numpy kept them
     for t, rec in c.get("steps", {}).items():
         t = int(t)
         r = rec["rank"]
-        np.testing.assert_allclose(res.sv[t, :r], rec["sv"][:r], rtol=1e-6)
+        if res.sv[t, 1] > 0 or r == 1:          # degenerate columns (fewer distinct points than k) report s_1 only
+            np.testing.assert_allclose(res.sv[t, :r], rec["sv"][:r], rtol=1e-6)
     dp.free()
 
 
@@ -103,7 +104,13 @@ def test_lazy_continuation_values(amc, golden, name):
         assert tt == t_o == t
         np.testing.assert_allclose(S_t, S_o, rtol=1e-13)
         scale = max(np.abs(cv_o).max(), 1e-12)
-        assert np.abs(cv - cv_o).max() <= 1e-8 * scale
+        # numpy's own fitted values carry an error ~ cond(kept part of A) * eps (LAPACK gelsd); the CUDA solver was
+        # checked against the exact truncated projection to 1e-14 (tests/test_solver_host.py, DESIGN.md "Solver").
+        tol = 1e-9
+        if t < n:
+            d = o.steps[t]
+            tol = max(tol, 20 * d["sv"][0] / d["sv"][d["rank"] - 1] * 2.2e-16)
+        assert np.abs(cv - cv_o).max() <= tol * scale, (t, tol)
     assert (cont[-1][2] == 0).all()
 
 
@@ -173,9 +180,15 @@ def test_small_array_ops(amc):
     Y = np.maximum(100 - X, 0) + rng.standard_normal(X.size)
     for basis, deg, kw in [("Power", 3, {}), ("Chebyshev", 4, {}), ("Legendre", 6, dict(scaling=True)),
                            ("Chebyshev", 10, dict(scaling=True, scaling_factor=1))]:
-        want = orc.regression_fit(X, Y, basis, deg, **kw)
+        diag = {}
+        want = orc.regression_fit(X, Y, basis, deg, diag=diag, **kw)
         got = amc.regression_estimate(X, Y, basis, deg, **kw)
-        assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max()
+        tol = max(1e-9, 20 * diag["sv"][0] / diag["sv"][diag["rank"] - 1] * 2.2e-16)   # numpy's own error
+        assert np.abs(got - want).max() <= tol * np.abs(want).max()
+        U_ = (X - diag["centre"]) / (kw.get("scaling_factor", 2) * diag["spread"]) if kw.get("scaling") else X
+        Us = np.linalg.svd(orc.basis_matrix(U_, basis, deg), full_matrices=False)[0][:, :diag["rank"]]
+        exact = Us @ (Us.T @ Y)                                                       # exact projection
+        assert np.abs(got - exact).max() <= max(1e-9, tol / 10) * np.abs(want).max()
         A = amc.get_basis_polynomials(X[:100] / 100, basis, deg)
         np.testing.assert_allclose(A, orc.basis_matrix(X[:100] / 100, basis, deg), rtol=1e-11, atol=1e-13)
     paths = orc.generate_asset_paths(100, 0.01, 0.2, 1.0, 20, 500)
