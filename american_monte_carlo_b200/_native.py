@@ -20,7 +20,7 @@ class LsmSpec(C.Structure):
     _fields_ = [("K", C.c_double), ("r", C.c_double), ("dt", C.c_double), ("barrier", C.c_double),
                 ("scaling_factor", C.c_double), ("is_put", C.c_int), ("is_american", C.c_int), ("basis", C.c_int),
                 ("degree", C.c_int), ("scaling", C.c_int), ("want_regression", C.c_int),
-                ("want_exercise_steps", C.c_int), ("reserved", C.c_int)]
+                ("want_exercise_steps", C.c_int), ("want_svd", C.c_int)]
 
 
 class LsmSteps(C.Structure):

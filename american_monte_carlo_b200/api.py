@@ -275,7 +275,7 @@ def _as_device_paths(paths, ctx):
 
 def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="European", basis_type="Chebyshev",
               degree=4, scaling=False, scaling_factor=2, *, want_regression=None, want_exercise_steps=False,
-              want_cashflows=False, profile=False, ctx: Context | None = None) -> LsmResult:
+              want_cashflows=False, want_svd=False, profile=False, ctx: Context | None = None) -> LsmResult:
     """One backward sweep (amc.py:139-197) with all diagnostics.  `lsmc_option_pricing` is the reference-shaped wrapper."""
     ctx = ctx or default_context()
     dp, temporary = _as_device_paths(paths, ctx)
@@ -291,7 +291,7 @@ def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="E
                          scaling_factor=float(scaling_factor), is_put=int(option_type == "Put"),    # amc.py:86
                          is_american=int(american), basis=N.BASIS_ID.get(basis_type, 0), degree=int(degree),
                          scaling=int(bool(scaling)), want_regression=int(bool(want_regression)),
-                         want_exercise_steps=int(bool(want_exercise_steps)), reserved=0)
+                         want_exercise_steps=int(bool(want_exercise_steps)), want_svd=int(bool(want_svd)))
         rows = n + 1
         st = dict(gamma=np.zeros((rows, N.AMC_MAX_K)), beta=np.zeros((rows, N.AMC_MAX_K)),
                   sv=np.zeros((rows, N.AMC_MAX_K)), mean_x=np.zeros(rows), std_x=np.zeros(rows),

@@ -621,6 +621,7 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     sspec.degree = D;
     sspec.basis = spec->basis;
     sspec.scaling = spec->scaling;
+    sspec.want_svd = spec->want_svd;
     sspec.scaling_factor = spec->scaling_factor;
     sspec.n_paths = Pg;
 
@@ -858,6 +859,7 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     s.spec.degree = degree;
     s.spec.basis = basis;
     s.spec.scaling = scaling;
+    s.spec.want_svd = 0;
     s.spec.scaling_factor = scaling_factor;
     s.spec.n_paths = (double)n;
     s.y_scale = 1.0;

@@ -165,9 +165,10 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_kernel(const StepArgs a
 //   phase 2 (do_solve):  thread 0 runs the k x k solve and stores gamma / diagnostics.
 //   final_price:         price = sum(U) / P.
 // Multi-GPU: phase 1, then an NCCL all-reduce of `sums`, then phase 2 as a second launch.
-__global__ void __launch_bounds__(128) lsm_solve_kernel(const SolveArgs a) {
-    const int d = a.spec.degree;
-    const int nacc = 3 * d + 1;
+template <int K>
+__global__ void __launch_bounds__(128, 1) lsm_solve_kernel(const SolveArgs a) {
+    constexpr int d = K - 1;
+    constexpr int nacc = 3 * d + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.do_reduce) {
         for (int acc = warp; acc < nacc; acc += 4) {
@@ -177,7 +178,6 @@ __global__ void __launch_bounds__(128) lsm_solve_kernel(const SolveArgs a) {
             if (lane == 0) a.sums[acc] = v;
         }
         __syncthreads();
-        __threadfence();
     }
     if (threadIdx.x != 0) return;
     if (a.final_price) {
@@ -185,12 +185,15 @@ __global__ void __launch_bounds__(128) lsm_solve_kernel(const SolveArgs a) {
         return;
     }
     if (!a.do_solve) return;
-    double h[2 * kMaxK], g[kMaxK];
+    double h[2 * d + 1], g[K];
     h[0] = a.spec.n_paths;
+#pragma unroll
     for (int m = 1; m <= 2 * d; ++m) h[m] = a.sums[m - 1];
+#pragma unroll
     for (int m = 0; m <= d; ++m) g[m] = a.sums[2 * d + m];
     SolveResult res;
-    lsm_solve(a.spec, h, g, a.y_scale, a.mu_ref, a.sigma_ref, &res);
+    lsm_solve_t<K>(a.spec, h, g, a.y_scale, a.mu_ref, a.sigma_ref, &res);
+#pragma unroll
     for (int i = 0; i < kMaxK; ++i) {
         a.gamma[i] = res.gamma[i];
         if (a.beta) a.beta[i] = res.beta[i];
@@ -311,7 +314,20 @@ int step_grid_size(int dtype, int degree, int sm_count) {
 }
 
 cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s) {
-    lsm_solve_kernel<<<1, 128, 0, s>>>(a);
+    switch (a.spec.degree) {
+        case 0: lsm_solve_kernel<1><<<1, 128, 0, s>>>(a); break;
+        case 1: lsm_solve_kernel<2><<<1, 128, 0, s>>>(a); break;
+        case 2: lsm_solve_kernel<3><<<1, 128, 0, s>>>(a); break;
+        case 3: lsm_solve_kernel<4><<<1, 128, 0, s>>>(a); break;
+        case 4: lsm_solve_kernel<5><<<1, 128, 0, s>>>(a); break;
+        case 5: lsm_solve_kernel<6><<<1, 128, 0, s>>>(a); break;
+        case 6: lsm_solve_kernel<7><<<1, 128, 0, s>>>(a); break;
+        case 7: lsm_solve_kernel<8><<<1, 128, 0, s>>>(a); break;
+        case 8: lsm_solve_kernel<9><<<1, 128, 0, s>>>(a); break;
+        case 9: lsm_solve_kernel<10><<<1, 128, 0, s>>>(a); break;
+        case 10: lsm_solve_kernel<11><<<1, 128, 0, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -112,14 +112,16 @@ typedef struct amc_lsm_spec {
     int want_regression;     /* run the per-step regressions even when they cannot change the price
                                 (European exercise): needed for continuation values, amc.py:151,164 */
     int want_exercise_steps; /* keep a per-path exercise-step array on the device (tests / diagnostics) */
-    int reserved;
+    int want_svd;            /* always run the k x k SVD and report singular values (otherwise it is skipped on
+                                steps whose full rank is certified cheaply; prices do not depend on this) */
 } amc_lsm_spec;
 
 /* per-step diagnostics, all indexed by t = 0..n_time_steps (entry n is unused: no regression at maturity) */
 typedef struct amc_lsm_steps {
     double* gamma;   /* [(n+1)][AMC_MAX_K] continuation polynomial in z = (x - mu_t)/sigma_t (internal basis) */
     double* beta;    /* [(n+1)][AMC_MAX_K] numpy-lstsq-equivalent coefficients in the user's basis */
-    double* sv;      /* [(n+1)][AMC_MAX_K] singular values of the design matrix, descending */
+    double* sv;      /* [(n+1)][AMC_MAX_K] singular values of the design matrix, descending (rows where the
+                        SVD ran: always with spec.want_svd, else only on steps that were not certified) */
     double* mean_x;  /* [(n+1)] np.mean(paths[:, t]) */
     double* std_x;   /* [(n+1)] np.std(paths[:, t]) */
     int* rank;       /* [(n+1)] numpy's rank */

@@ -4,12 +4,18 @@
 // with numpy.linalg.lstsq without a GPU.
 #include "../../american_monte_carlo_b200/csrc/lsm_solve.h"
 
-extern "C" int amc_test_lsm_solve(int degree, int basis, int scaling, double scaling_factor, double n_paths,
+extern "C" int amc_test_lsm_solve(int degree, int basis, int scaling, int want_svd, double scaling_factor, double n_paths,
                                   const double* h, const double* g, double y_scale, double mu_ref,
                                   double sigma_ref, double* gamma, double* beta, double* sv, double* stats,
                                   int* info) {
     if (degree < 0 || degree > amc::kMaxDegree) return 1;
-    amc::SolveSpec spec{degree, basis, scaling, scaling_factor, n_paths};
+    amc::SolveSpec spec;
+    spec.degree = degree;
+    spec.basis = basis;
+    spec.scaling = scaling;
+    spec.want_svd = want_svd;
+    spec.scaling_factor = scaling_factor;
+    spec.n_paths = n_paths;
     amc::SolveResult res;
     amc::lsm_solve(spec, h, g, y_scale, mu_ref, sigma_ref, &res);
     for (int i = 0; i <= degree; ++i) { gamma[i] = res.gamma[i]; beta[i] = res.beta[i]; sv[i] = res.sv[i]; }

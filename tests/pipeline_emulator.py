@@ -27,7 +27,7 @@ def host_solver():
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src])
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)
-    lib.amc_test_lsm_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+    lib.amc_test_lsm_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                        dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                        dp, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]
     lib.amc_test_lsm_solve.restype = ctypes.c_int
@@ -37,7 +37,7 @@ def host_solver():
 _LIB = None
 
 
-def solve(degree, basis, scaling, scaling_factor, n_paths, h, g, y_scale, mu_ref, sigma_ref):
+def solve(degree, basis, scaling, scaling_factor, n_paths, h, g, y_scale, mu_ref, sigma_ref, want_svd=True):
     global _LIB
     if _LIB is None:
         _LIB = host_solver()
@@ -47,7 +47,8 @@ def solve(degree, basis, scaling, scaling_factor, n_paths, h, g, y_scale, mu_ref
     gamma = np.zeros(k); beta = np.zeros(k); sv = np.zeros(k); stats = np.zeros(2)
     info = (ctypes.c_int * 3)()
     dp = ctypes.POINTER(ctypes.c_double)
-    rc = _LIB.amc_test_lsm_solve(degree, BASIS_ID[basis], int(bool(scaling)), float(scaling_factor), float(n_paths),
+    rc = _LIB.amc_test_lsm_solve(degree, BASIS_ID[basis], int(bool(scaling)), int(bool(want_svd)), float(scaling_factor),
+                                 float(n_paths),
                                  h.ctypes.data_as(dp), g.ctypes.data_as(dp), float(y_scale), float(mu_ref),
                                  float(sigma_ref), gamma.ctypes.data_as(dp), beta.ctypes.data_as(dp),
                                  sv.ctypes.data_as(dp), stats.ctypes.data_as(dp), info)
@@ -93,7 +94,7 @@ def column_maps(paths_tm):
 
 
 def price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="European", basis_type="Chebyshev",
-          degree=4, scaling=False, scaling_factor=2, maps=None, x_dtype=np.float64):
+          degree=4, scaling=False, scaling_factor=2, maps=None, x_dtype=np.float64, want_svd=True):
     """Returns dict(price, tau, U, ranks, gammas).  `paths` is [P, n+1] like the reference's."""
     P, n1 = paths.shape
     n = n1 - 1
@@ -113,16 +114,16 @@ def price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="Europ
 
     U = np.where(first <= n, intrinsic(S[n]) * np.exp(-rdt * n), 0.0)       # discounted to time 0
     tau = np.full(P, n)
-    ranks = {}; gammas = {}
+    ranks = {}; gammas = {}; sweeps = {}
     for t in range(n - 1, -1, -1):
         z = (S[t] - mu[t]) * (1.0 / sg[t])
         h, g = moments(z, U, degree)
-        res = solve(degree, basis_type, scaling, scaling_factor, P, h, g, np.exp(rdt * t), mu[t], sg[t])
-        ranks[t] = res["rank"]; gammas[t] = res["gamma"]
+        res = solve(degree, basis_type, scaling, scaling_factor, P, h, g, np.exp(rdt * t), mu[t], sg[t], want_svd)
+        ranks[t] = res["rank"]; gammas[t] = res["gamma"]; sweeps[t] = res["sweeps"]
         if american:
             fit = horner(res["gamma"], z)
             iv = intrinsic(S[t])
             take = (first <= t) & (iv > 0) & (iv > fit)
             U = np.where(take, iv * np.exp(-rdt * t), U)
             tau = np.where(take, t, tau)
-    return dict(price=U.sum() / P, tau=tau, U=U, ranks=ranks, gammas=gammas)
+    return dict(price=U.sum() / P, tau=tau, U=U, ranks=ranks, gammas=gammas, sweeps=sweeps)

@@ -40,7 +40,7 @@ def test_injected_normals_price_decisions_and_ranks(amc, golden, name):
     got_paths = np.asarray(dp)
     assert np.max(np.abs(got_paths - paths) / paths) < 1e-13         # log-space sum vs cumprod: ~3e-15
     res = amc.lsm_price(dp, *price_args(c), **c["kwargs"], want_exercise_steps=True, want_cashflows=True,
-                        want_regression=True)
+                        want_regression=True, want_svd=True)
     n = c["n_time_steps"]
     flips = int((res.exercise_steps != o.exercise_times).sum())
     assert flips == 0, f"{flips} paths exercise at a different step"
