@@ -1,0 +1,37 @@
+"""GPU tier, >= 2 GPUs: path sharding + per-step NCCL all-reduce of the moment sums."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_workers(n):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29653", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
+    return json.loads(line[len("MGPU_RESULT "):])
+
+
+def test_sharded_sweep_equals_single_gpu_and_oracle(libamc_path):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = run_workers(min(n, 8) if n in (2, 4, 8) else 2)
+    inj = out["injected"]
+    assert inj["flips"] == 0 and inj["ranks_equal"]
+    assert abs(inj["price"] - inj["oracle"]) <= 1e-10 * inj["oracle"]
+    ph = out["philox"]
+    assert abs(ph["multi"] - ph["single"]) <= 1e-11 * ph["single"]
+    assert ph["gamma_max_rel"] < 1e-9
+    assert out["gamma_identical_across_ranks"]
+    ad = out["adopted"]
+    assert abs(ad["price"] - inj["oracle"]) <= 1e-10 * inj["oracle"]
+    assert ad["mu_err"] < 1e-12 and ad["sg_err"] < 1e-10
