@@ -10,6 +10,7 @@
 #include <nccl.h>      // types and enums only: the library is resolved at run time
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -537,8 +538,8 @@ static int check_spec(const amc_lsm_spec* s) {
 static int step_grid(amc_ctx* c, int dtype, int degree, int64_t n_paths) {
     int& g = c->grid_cache[dtype][degree];
     if (g == 0) g = step_grid_size(dtype, degree, c->sm_count);
-    // small path sets: no more blocks than there are pairs of paths to hand out
-    int64_t need = ((n_paths + 1) / 2 + kStepThreads - 1) / kStepThreads;
+    // small path sets: no more blocks than there are tiles of 1024 paths to hand out
+    int64_t need = (n_paths + 1023) / 1024;
     if (need < 1) need = 1;
     return (int)(need < g ? need : g);
 }
@@ -600,6 +601,9 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     if (barrier && P > 0)
         CU(launch_first_hit(dtype, p->S, p->ld, n + 1, P, spec->barrier, fh, c->stream));
 
+    // L2 management knobs (on by default; AMC_L2_REVERSE=0 / AMC_L2_HINTS=0 for A/B measurements)
+    static const int opt_reverse = getenv("AMC_L2_REVERSE") ? atoi(getenv("AMC_L2_REVERSE")) : 1;
+    static const int opt_hints = getenv("AMC_L2_HINTS") ? atoi(getenv("AMC_L2_HINTS")) : 1;
     EventPool pool{c};
     cudaEvent_t ev_start, ev_stop;
     if ((rc = pool.get(&ev_start)) || (rc = pool.get(&ev_stop))) return rc;
@@ -639,6 +643,8 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         a.mode = mode;
         a.moments = moments ? 1 : 0;
         a.is_put = spec->is_put;
+        a.reverse = opt_reverse ? (t & 1) : 0;
+        a.l2_hints = opt_hints;
         a.K = spec->K;
         a.disc_dec = exp(-rdt * (double)t);
         a.mu_dec = p->mu[t];

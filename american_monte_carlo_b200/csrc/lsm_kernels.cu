@@ -13,6 +13,8 @@
 // State: U[p] = cashflow of path p discounted to time 0 (= cashflows * exp(-r dt exercise_times) of
 // amc.py:128,196, which the reference recomputes at every step).  The regression target at step t is
 // Y = U * exp(r dt t); the scalar factor is applied to the reduced sums, not per path.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -52,8 +54,9 @@ __device__ __forceinline__ double horner(const double (&gam)[D + 1], double z) {
 
 // One path: decision at t_dec, then moments at t_dec-1.  All flags are launch-uniform.
 template <int D>
-__device__ __forceinline__ void path_step(const StepArgs& a, const double (&gam)[D + 1], double xd, double xr,
+__device__ __forceinline__ bool path_step(const StepArgs& a, const double (&gam)[D + 1], double xd, double xr,
                                           double& u, int& tau, int fh, double (&acc)[3 * D + 1]) {
+    bool changed = false;
     if (a.mode != kObserve) {
         const double iv = a.is_put ? (a.K - xd) : (xd - a.K);
         const bool in = (fh <= a.t_dec);
@@ -61,6 +64,7 @@ __device__ __forceinline__ void path_step(const StepArgs& a, const double (&gam)
             // cashflows[hit] = max(payoff, 0), exercise_times[hit] = n; everything else stays 0 / n
             u = (in && iv > 0.0) ? iv * a.disc_dec : 0.0;
             tau = a.t_dec;
+            changed = true;
         } else {
             const double zd = (xd - a.mu_dec) * a.isg_dec;
             const double fit = horner<D>(gam, zd);
@@ -68,6 +72,7 @@ __device__ __forceinline__ void path_step(const StepArgs& a, const double (&gam)
             if (in && iv > 0.0 && iv > fit) {
                 u = iv * a.disc_dec;
                 tau = a.t_dec;
+                changed = true;
             }
         }
     }
@@ -77,6 +82,7 @@ __device__ __forceinline__ void path_step(const StepArgs& a, const double (&gam)
     } else {
         acc[2 * D] += u;
     }
+    return changed;
 }
 
 template <typename XT, int D>
@@ -154,6 +160,134 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_kernel(const StepArgs a
             a.U[p] = u;
             if (a.tau) a.tau[p] = tau;
         }
+    }
+    block_reduce_store<NACC, kStepThreads>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-pipelined variant of the step kernel (the default).  Each persistent block owns a ring of kStages shared-
+// memory stages; one elected thread issues 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) of the next
+// tiles of S_t, S_{t-1} and U while all 8 warps compute on the current tile, completion signalled through
+// mbarriers (complete_tx).  Loads therefore live in shared memory instead of registers: the bytes in flight per
+// SM are set by the ring (kStages x 24 KB at f64), not by occupancy x registers, which is what limited the
+// register-staged kernel above to 0.79 of the copy roofline (ncu: 108 registers, 25 % occupancy).
+// The updated state goes straight from registers to global memory (coalesced 16-byte stores).
+constexpr int kTile = 1024;       // paths per tile
+constexpr int kStages = 4;
+
+template <typename XT>
+struct StageBytes { static constexpr int value = kTile * (2 * (int)sizeof(XT) + 8); };
+
+template <typename XT, int D>
+__global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepArgs a) {
+    constexpr int NACC = 3 * D + 1;
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ double red[(kStepThreads / 32) * NACC];
+    __shared__ uint64_t full[kStages];
+
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    double gam[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) gam[i] = (a.mode == kDecide) ? a.coef[i] : 0.0;
+
+    const XT* xdec = static_cast<const XT*>(a.x_dec);
+    const XT* xreg = static_cast<const XT*>(a.x_reg);
+    const bool need_dec = (a.mode != kObserve);
+    const bool need_u_in = (a.mode != kMaturity);
+    const bool write_u = (a.mode != kObserve);
+
+    const int64_t n_tiles = (a.n_paths + kTile - 1) / kTile;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles blockIdx.x + i*grid
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    auto tile_of = [&](int i) -> int64_t {
+        const int64_t fwd = blockIdx.x + (int64_t)i * gridDim.x;
+        return a.reverse ? (n_tiles - 1 - fwd) : fwd;
+    };
+    auto issue = [&](int i) {           // thread 0 only: start the copies of this block's i-th tile
+        const int64_t tile = tile_of(i);
+        const int64_t p0 = tile * kTile;
+        int64_t valid = a.n_paths - p0;
+        if (valid > kTile) valid = kTile;
+        const uint32_t elems = (uint32_t)((valid + 31) / 32 * 32);     // columns are padded to 32 elements
+        const int s = i % kStages;
+        unsigned char* st = ring + (size_t)s * StageBytes<XT>::value;
+        const uint32_t bx = elems * (uint32_t)sizeof(XT), bu = elems * 8u;
+        const uint32_t total = (need_dec ? bx : 0u) + (a.moments ? bx : 0u) + (need_u_in ? bu : 0u);
+        mbar_expect_tx(&full[s], total);
+        if (a.l2_hints) {
+            // S_t is dead after this launch; S_{t-1} and U are re-read by the next launch
+            if (need_dec) tma_load_1d_hint(st, xdec + p0, bx, &full[s], pol_stream);
+            if (a.moments) tma_load_1d_hint(st + kTile * sizeof(XT), xreg + p0, bx, &full[s], pol_keep);
+            if (need_u_in) tma_load_1d_hint(st + 2 * kTile * sizeof(XT), a.U + p0, bu, &full[s], pol_keep);
+        } else {
+            if (need_dec) tma_load_1d(st, xdec + p0, bx, &full[s]);
+            if (a.moments) tma_load_1d(st + kTile * sizeof(XT), xreg + p0, bx, &full[s]);
+            if (need_u_in) tma_load_1d(st + 2 * kTile * sizeof(XT), a.U + p0, bu, &full[s]);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages - 1 && i < my_tiles; ++i) issue(i);
+    }
+
+    using V2 = typename Vec2<XT>::type;
+    for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % kStages;
+        if (threadIdx.x == 0 && i + kStages - 1 < my_tiles) issue(i + kStages - 1);
+        mbar_wait(&full[s], (uint32_t)((i / kStages) & 1));
+
+        const int64_t tile = tile_of(i);
+        const int64_t p0 = tile * kTile;
+        int64_t valid64 = a.n_paths - p0;
+        const int valid = (int)(valid64 > kTile ? kTile : valid64);
+        const unsigned char* st = ring + (size_t)s * StageBytes<XT>::value;
+        const V2* sxd = reinterpret_cast<const V2*>(st);
+        const V2* sxr = reinterpret_cast<const V2*>(st + kTile * sizeof(XT));
+        const double2* su = reinterpret_cast<const double2*>(st + 2 * kTile * sizeof(XT));
+
+#pragma unroll
+        for (int k = 0; k < kTile / 2 / kStepThreads; ++k) {
+            const int j = threadIdx.x + k * kStepThreads;        // pair index inside the tile
+            const int e0 = 2 * j;
+            if (e0 < valid) {
+                const bool two = (e0 + 1 < valid);
+                double xd0 = 0, xd1 = 0, xr0 = 0, xr1 = 0;
+                double2 u = make_double2(0.0, 0.0);
+                int2 f = make_int2(0, 0), t = make_int2(0, 0);
+                if (need_dec) { const V2 v = sxd[j]; xd0 = (double)v.x; xd1 = (double)v.y; }
+                if (a.moments) { const V2 v = sxr[j]; xr0 = (double)v.x; xr1 = (double)v.y; }
+                if (need_u_in) u = su[j];
+                const int64_t p = p0 + e0;
+                if (a.first_hit) { f.x = __ldg(a.first_hit + p); if (two) f.y = __ldg(a.first_hit + p + 1); }
+                if (a.tau && need_u_in) { t.x = a.tau[p]; if (two) t.y = a.tau[p + 1]; }
+                bool changed = path_step<D>(a, gam, xd0, xr0, u.x, t.x, f.x, acc);
+                if (two) changed |= path_step<D>(a, gam, xd1, xr1, u.y, t.y, f.y, acc);
+                // the state is written only where a path exercised (16-byte granularity): below maturity
+                // most pairs are untouched, which removes most of the write traffic
+                if (write_u && changed) {
+                    if (two) {
+                        if (a.l2_hints) st_hint(reinterpret_cast<double2*>(a.U + p), u, pol_keep);
+                        else *reinterpret_cast<double2*>(a.U + p) = u;
+                        if (a.tau) *reinterpret_cast<int2*>(a.tau + p) = t;
+                    } else {
+                        if (a.l2_hints) st_hint(a.U + p, u.x, pol_keep);
+                        else a.U[p] = u.x;
+                        if (a.tau) a.tau[p] = t.x;
+                    }
+                }
+            }
+        }
+        __syncthreads();                 // every warp is done with stage s before it is refilled
     }
     block_reduce_store<NACC, kStepThreads>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
 }
@@ -253,9 +387,30 @@ __global__ void basis_matrix_kernel(const double* __restrict__ X, int64_t n, int
 
 // ---------------------------------------------------------------------------------------------------------
 // launchers
+// AMC_STEP_KERNEL=ldg selects the register-staged kernel (kept for A/B measurements); default is the TMA ring.
+static bool use_tma_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AMC_STEP_KERNEL");
+        v = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <typename XT, int D>
 static cudaError_t launch_step_t(int grid, const StepArgs& a, cudaStream_t s) {
-    lsm_step_kernel<XT, D><<<grid, kStepThreads, 0, s>>>(a);
+    if (use_tma_kernel()) {
+        constexpr int smem = kStages * StageBytes<XT>::value;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(lsm_step_tma_kernel<XT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        lsm_step_tma_kernel<XT, D><<<grid, kStepThreads, smem, s>>>(a);
+    } else {
+        lsm_step_kernel<XT, D><<<grid, kStepThreads, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -284,7 +439,13 @@ cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cuda
 template <typename XT, int D>
 static int occupancy_blocks() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lsm_step_kernel<XT, D>, kStepThreads, 0);
+    if (use_tma_kernel()) {
+        constexpr int smem = kStages * StageBytes<XT>::value;
+        cudaFuncSetAttribute(lsm_step_tma_kernel<XT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lsm_step_tma_kernel<XT, D>, kStepThreads, smem);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lsm_step_kernel<XT, D>, kStepThreads, 0);
+    }
     return nb;
 }
 

@@ -198,7 +198,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     import american_monte_carlo_b200 as amc
     from american_monte_carlo_b200 import _native as N
@@ -300,8 +301,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        for _ in range(args.warmup):           # nvidia-smi needs a moment before its first sample
-            one_step(False)
+    for _ in range(args.warmup):               # every rank (collectives inside); nvidia-smi needs a moment
+        one_step(False)
+    if rank == 0:
         time.sleep(0.25)
         sampler.mark("begin")
     ms_dev, res_dev = timed(False, args.steps)

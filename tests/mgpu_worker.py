@@ -18,7 +18,8 @@ from oracle import lsm_oracle as orc  # noqa: E402
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     rank, world = dist.get_rank(), dist.get_world_size()
     ctx = init_distributed()
     out = {}
