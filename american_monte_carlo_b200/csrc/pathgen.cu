@@ -122,35 +122,75 @@ cudaError_t launch_generate_philox(int dtype, void* S, int64_t ld, int n_steps, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1z: block = 128 paths; Z is consumed in tiles of 32 steps staged in shared memory.
+// K1z: block = 128 paths (one per thread); Z is consumed in tiles of kZSteps steps.  The tile of the NEXT step
+// block is fetched with cp.async (LDGSTS, 16-byte chunks, coalesced along each path's row) into the second half
+// of a double buffer while the current tile is turned into prices, so the row-major read of Z, the FP64 exp and
+// the timestep-major write of S overlap instead of alternating.
 constexpr int kZPaths = 128;
-constexpr int kZSteps = 32;
+constexpr int kZSteps = 16;
+constexpr int kZPitch = kZSteps + 2;        // doubles per shared row: 16-byte aligned rows, spreads the banks
 
-template <typename XT>
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename XT, bool WIDE>
 __global__ void __launch_bounds__(kZPaths) normals_paths_kernel(const double* __restrict__ Z, XT* __restrict__ S,
                                                                 int64_t ld, int n_steps, int64_t n_local,
                                                                 GbmParams g) {
-    __shared__ double tile[kZSteps][kZPaths + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(16) double tile[2][kZPaths][kZPitch];
+    const int n_tiles = (n_steps + kZSteps - 1) / kZSteps;
+
+    auto fetch = [&](int64_t pb, int k, int buf) {
+        const int t0 = k * kZSteps;
+        const int cols = min(kZSteps, n_steps - t0);
+        if (WIDE) {
+            // 16-byte chunks: chunk c of row r; consecutive threads walk along a row first (coalesced)
+            constexpr int CH = kZSteps / 2;
+            for (int idx = threadIdx.x; idx < kZPaths * CH; idx += kZPaths) {
+                const int r = idx / CH, c = idx % CH;
+                if (pb + r < n_local && 2 * c < cols)            // n_steps is even in WIDE mode: chunks are whole
+                    cp_async_16(&tile[buf][r][2 * c], Z + (pb + r) * n_steps + t0 + 2 * c);
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < kZPaths * kZSteps; idx += kZPaths) {
+                const int r = idx / kZSteps, c = idx % kZSteps;
+                if (pb + r < n_local && c < cols) cp_async_8(&tile[buf][r][c], Z + (pb + r) * n_steps + t0 + c);
+            }
+        }
+        cp_async_commit();
+    };
+
     for (int64_t pb = (int64_t)blockIdx.x * kZPaths; pb < n_local; pb += (int64_t)gridDim.x * kZPaths) {
         const int64_t p = pb + threadIdx.x;
         double L = 0.0;
         if (p < n_local) S[p] = (XT)g.S0;
-        for (int t0 = 0; t0 < n_steps; t0 += kZSteps) {
-            __syncthreads();
-            // each warp loads 32 rows (paths); a row segment of 32 steps is 256 contiguous bytes
-            for (int r = warp; r < kZPaths; r += kZPaths / 32) {
-                const int64_t pr = pb + r;
-                if (pr < n_local && t0 + lane < n_steps) tile[lane][r] = __ldg(Z + pr * n_steps + t0 + lane);
+        fetch(pb, 0, 0);
+        for (int k = 0; k < n_tiles; ++k) {
+            const int buf = k & 1;
+            if (k + 1 < n_tiles) {
+                fetch(pb, k + 1, buf ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
             __syncthreads();
             if (p < n_local) {
+                const int t0 = k * kZSteps;
                 const int jmax = min(kZSteps, n_steps - t0);
+#pragma unroll 4
                 for (int j = 0; j < jmax; ++j) {
-                    L += fma(g.vol, tile[j][threadIdx.x], g.drift);
+                    L += fma(g.vol, tile[buf][threadIdx.x][j], g.drift);
                     S[(int64_t)(t0 + j + 1) * ld + p] = (XT)(g.S0 * exp(L));
                 }
             }
+            __syncthreads();             // the buffer is refilled two iterations later
         }
     }
 }
@@ -158,12 +198,17 @@ __global__ void __launch_bounds__(kZPaths) normals_paths_kernel(const double* __
 cudaError_t launch_from_normals(int dtype, const double* Z_dev, void* S, int64_t ld, int n_steps, int64_t n_local,
                                 GbmParams g, cudaStream_t s) {
     int64_t blocks = (n_local + kZPaths - 1) / kZPaths;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks < 1) blocks = 1;
-    if (dtype == 1)
-        normals_paths_kernel<float><<<(int)blocks, kZPaths, 0, s>>>(Z_dev, (float*)S, ld, n_steps, n_local, g);
-    else
-        normals_paths_kernel<double><<<(int)blocks, kZPaths, 0, s>>>(Z_dev, (double*)S, ld, n_steps, n_local, g);
+    const bool wide = (n_steps % 2 == 0) && (((uintptr_t)Z_dev & 15) == 0);
+    const int b = (int)blocks;
+    if (dtype == 1) {
+        if (wide) normals_paths_kernel<float, true><<<b, kZPaths, 0, s>>>(Z_dev, (float*)S, ld, n_steps, n_local, g);
+        else normals_paths_kernel<float, false><<<b, kZPaths, 0, s>>>(Z_dev, (float*)S, ld, n_steps, n_local, g);
+    } else {
+        if (wide) normals_paths_kernel<double, true><<<b, kZPaths, 0, s>>>(Z_dev, (double*)S, ld, n_steps, n_local, g);
+        else normals_paths_kernel<double, false><<<b, kZPaths, 0, s>>>(Z_dev, (double*)S, ld, n_steps, n_local, g);
+    }
     return cudaGetLastError();
 }
 
