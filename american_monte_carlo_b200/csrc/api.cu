@@ -604,6 +604,10 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     // L2 management knobs (on by default; AMC_L2_REVERSE=0 / AMC_L2_HINTS=0 for A/B measurements)
     static const int opt_reverse = getenv("AMC_L2_REVERSE") ? atoi(getenv("AMC_L2_REVERSE")) : 1;
     static const int opt_hints = getenv("AMC_L2_HINTS") ? atoi(getenv("AMC_L2_HINTS")) : 1;
+    // programmatic dependent launch along the K3 -> K4 -> K3 chain (single GPU, not while profiling: the
+    // per-launch events and the NCCL kernels are ordinary stream dependencies)
+    static const int opt_pdl = getenv("AMC_PDL") ? atoi(getenv("AMC_PDL")) : 1;
+    const bool pdl = opt_pdl && !profile && c->world == 1;
     EventPool pool{c};
     cudaEvent_t ev_start, ev_stop;
     if ((rc = pool.get(&ev_start)) || (rc = pool.get(&ev_stop))) return rc;
@@ -653,7 +657,7 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         a.isg_reg = moments ? 1.0 / p->sigma[t - 1] : 1.0;
         int r2;
         if ((r2 = bracket(step_ev))) return r2;
-        CU(launch_step(dtype, D, grid, a, c->stream));
+        CU(launch_step(dtype, D, grid, a, c->stream, pdl && n_step > 0));
         if ((r2 = bracket(step_ev))) return r2;
         ++n_step;
         return AMC_OK;
@@ -682,7 +686,7 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
             s.do_reduce = 1;
             s.do_solve = final_price ? 0 : 1;
             s.final_price = final_price ? 1 : 0;
-            CU(launch_solve(s, c->stream));
+            CU(launch_solve(s, c->stream, pdl));
             ++n_solve;
         } else {
             s.do_reduce = 1; s.do_solve = 0;

@@ -79,6 +79,16 @@ __device__ __forceinline__ void block_reduce_store(const double (&acc)[NACC], do
 
 }  // namespace amc
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// The sweep is a chain K3 -> K4 -> K3 -> ... of strictly dependent launches.  Launched with the
+// programmatic-stream-serialization attribute, a kernel's blocks may become resident while its predecessor is
+// still running; pdl_wait() then blocks until the predecessor has completed and flushed its memory.  Both are
+// no-ops for a kernel launched the ordinary way.
+namespace amc {
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+}  // namespace amc
+
 // ---- TMA (bulk async copy) + mbarrier helpers, sm_90+/sm_100a -----------------------------------------------
 // 1-D bulk copies need no tensor map: cp.async.bulk moves `bytes` (multiple of 16, 16-byte aligned on both
 // sides) global -> shared and signals completion on an mbarrier via complete_tx.  SASS: UBLKCP.

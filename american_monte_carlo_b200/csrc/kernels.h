@@ -58,8 +58,9 @@ struct SolveArgs {
 };
 
 int step_grid_size(int dtype, int degree, int sm_count);
-cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s);
-cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s);
+// pdl: launch as a programmatic dependent of the previous kernel in the stream (see common.cuh)
+cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s, bool pdl = false);
+cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl = false);
 cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const double* gamma_dev, int degree, double mu,
                                 double isg, int clamp, double* out_dev, cudaStream_t s);
 cudaError_t launch_intrinsic(const double* S_dev, int64_t n, double K, int is_put, double* out_dev, cudaStream_t s);

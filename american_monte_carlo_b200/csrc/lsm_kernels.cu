@@ -185,6 +185,9 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
     __shared__ double red[(kStepThreads / 32) * NACC];
     __shared__ uint64_t full[kStages];
 
+    pdl_launch_dependents();     // let the solve kernel of this step become resident right away
+    pdl_wait();                  // ... and do not touch memory before the previous solve has finished
+
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
@@ -304,6 +307,8 @@ __global__ void __launch_bounds__(128, 1) lsm_solve_kernel(const SolveArgs a) {
     constexpr int d = K - 1;
     constexpr int nacc = 3 * d + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     if (a.do_reduce) {
         for (int acc = warp; acc < nacc; acc += 4) {
             double v = 0.0;
@@ -397,8 +402,24 @@ static bool use_tma_kernel() {
     return v == 1;
 }
 
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, bool pdl,
+                             Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <typename XT, int D>
-static cudaError_t launch_step_t(int grid, const StepArgs& a, cudaStream_t s) {
+static cudaError_t launch_step_t(int grid, const StepArgs& a, cudaStream_t s, bool pdl) {
     if (use_tma_kernel()) {
         constexpr int smem = kStages * StageBytes<XT>::value;
         static bool configured = false;
@@ -407,7 +428,7 @@ static cudaError_t launch_step_t(int grid, const StepArgs& a, cudaStream_t s) {
             if (e != cudaSuccess) return e;
             configured = true;
         }
-        lsm_step_tma_kernel<XT, D><<<grid, kStepThreads, smem, s>>>(a);
+        return launch_ex(lsm_step_tma_kernel<XT, D>, grid, kStepThreads, smem, s, pdl, a);
     } else {
         lsm_step_kernel<XT, D><<<grid, kStepThreads, 0, s>>>(a);
     }
@@ -415,25 +436,25 @@ static cudaError_t launch_step_t(int grid, const StepArgs& a, cudaStream_t s) {
 }
 
 template <typename XT>
-static cudaError_t launch_step_d(int degree, int grid, const StepArgs& a, cudaStream_t s) {
+static cudaError_t launch_step_d(int degree, int grid, const StepArgs& a, cudaStream_t s, bool pdl) {
     switch (degree) {
-        case 0: return launch_step_t<XT, 0>(grid, a, s);
-        case 1: return launch_step_t<XT, 1>(grid, a, s);
-        case 2: return launch_step_t<XT, 2>(grid, a, s);
-        case 3: return launch_step_t<XT, 3>(grid, a, s);
-        case 4: return launch_step_t<XT, 4>(grid, a, s);
-        case 5: return launch_step_t<XT, 5>(grid, a, s);
-        case 6: return launch_step_t<XT, 6>(grid, a, s);
-        case 7: return launch_step_t<XT, 7>(grid, a, s);
-        case 8: return launch_step_t<XT, 8>(grid, a, s);
-        case 9: return launch_step_t<XT, 9>(grid, a, s);
-        case 10: return launch_step_t<XT, 10>(grid, a, s);
+        case 0: return launch_step_t<XT, 0>(grid, a, s, pdl);
+        case 1: return launch_step_t<XT, 1>(grid, a, s, pdl);
+        case 2: return launch_step_t<XT, 2>(grid, a, s, pdl);
+        case 3: return launch_step_t<XT, 3>(grid, a, s, pdl);
+        case 4: return launch_step_t<XT, 4>(grid, a, s, pdl);
+        case 5: return launch_step_t<XT, 5>(grid, a, s, pdl);
+        case 6: return launch_step_t<XT, 6>(grid, a, s, pdl);
+        case 7: return launch_step_t<XT, 7>(grid, a, s, pdl);
+        case 8: return launch_step_t<XT, 8>(grid, a, s, pdl);
+        case 9: return launch_step_t<XT, 9>(grid, a, s, pdl);
+        case 10: return launch_step_t<XT, 10>(grid, a, s, pdl);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s) {
-    return dtype == 1 ? launch_step_d<float>(degree, grid, a, s) : launch_step_d<double>(degree, grid, a, s);
+cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s, bool pdl) {
+    return dtype == 1 ? launch_step_d<float>(degree, grid, a, s, pdl) : launch_step_d<double>(degree, grid, a, s, pdl);
 }
 
 template <typename XT, int D>
@@ -474,19 +495,19 @@ int step_grid_size(int dtype, int degree, int sm_count) {
     return sm_count * nb;
 }
 
-cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s) {
+cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl) {
     switch (a.spec.degree) {
-        case 0: lsm_solve_kernel<1><<<1, 128, 0, s>>>(a); break;
-        case 1: lsm_solve_kernel<2><<<1, 128, 0, s>>>(a); break;
-        case 2: lsm_solve_kernel<3><<<1, 128, 0, s>>>(a); break;
-        case 3: lsm_solve_kernel<4><<<1, 128, 0, s>>>(a); break;
-        case 4: lsm_solve_kernel<5><<<1, 128, 0, s>>>(a); break;
-        case 5: lsm_solve_kernel<6><<<1, 128, 0, s>>>(a); break;
-        case 6: lsm_solve_kernel<7><<<1, 128, 0, s>>>(a); break;
-        case 7: lsm_solve_kernel<8><<<1, 128, 0, s>>>(a); break;
-        case 8: lsm_solve_kernel<9><<<1, 128, 0, s>>>(a); break;
-        case 9: lsm_solve_kernel<10><<<1, 128, 0, s>>>(a); break;
-        case 10: lsm_solve_kernel<11><<<1, 128, 0, s>>>(a); break;
+        case 0: return launch_ex(lsm_solve_kernel<1>, 1, 128, 0, s, pdl, a);
+        case 1: return launch_ex(lsm_solve_kernel<2>, 1, 128, 0, s, pdl, a);
+        case 2: return launch_ex(lsm_solve_kernel<3>, 1, 128, 0, s, pdl, a);
+        case 3: return launch_ex(lsm_solve_kernel<4>, 1, 128, 0, s, pdl, a);
+        case 4: return launch_ex(lsm_solve_kernel<5>, 1, 128, 0, s, pdl, a);
+        case 5: return launch_ex(lsm_solve_kernel<6>, 1, 128, 0, s, pdl, a);
+        case 6: return launch_ex(lsm_solve_kernel<7>, 1, 128, 0, s, pdl, a);
+        case 7: return launch_ex(lsm_solve_kernel<8>, 1, 128, 0, s, pdl, a);
+        case 8: return launch_ex(lsm_solve_kernel<9>, 1, 128, 0, s, pdl, a);
+        case 9: return launch_ex(lsm_solve_kernel<10>, 1, 128, 0, s, pdl, a);
+        case 10: return launch_ex(lsm_solve_kernel<11>, 1, 128, 0, s, pdl, a);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
