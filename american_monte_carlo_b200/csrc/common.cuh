@@ -59,7 +59,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Deterministic block reduction of NACC per-thread accumulators into out[0..NACC) (global memory, one row
 // per block).  Order is fixed by (lane, warp) -> bitwise reproducible for a given launch geometry.
-template <int NACC, int THREADS>
+template <int NACC, int THREADS, int ROW = NACC>
 __device__ __forceinline__ void block_reduce_store(const double (&acc)[NACC], double* smem /*[THREADS/32][NACC]*/,
                                                    double* out_row) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -69,10 +69,12 @@ __device__ __forceinline__ void block_reduce_store(const double (&acc)[NACC], do
         if (lane == 0) smem[warp * NACC + a] = v;
     }
     __syncthreads();
-    if (threadIdx.x < NACC) {
+    if (threadIdx.x < ROW) {                // ROW > NACC: the unused tail of the row is written as zero
         double v = 0.0;
+        if (threadIdx.x < NACC) {
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) v += smem[w * NACC + threadIdx.x];
+            for (int w = 0; w < THREADS / 32; ++w) v += smem[w * NACC + threadIdx.x];
+        }
         out_row[threadIdx.x] = v;
     }
 }

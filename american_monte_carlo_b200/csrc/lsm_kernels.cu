@@ -66,7 +66,7 @@ __device__ __forceinline__ bool path_step(const StepArgs& a, const double (&gam)
             tau = a.t_dec;
             changed = true;
         } else {
-            const double zd = (xd - a.mu_dec) * a.isg_dec;
+            const double zd = fma(xd, a.isg_dec, -a.mu_dec * a.isg_dec);
             const double fit = horner<D>(gam, zd);
             // candidates: knocked in AND in the money; exercise iff payoff > max(fit, 0)  (strict)
             if (in && iv > 0.0 && iv > fit) {
@@ -77,7 +77,7 @@ __device__ __forceinline__ bool path_step(const StepArgs& a, const double (&gam)
         }
     }
     if (a.moments) {
-        const double zr = (xr - a.mu_reg) * a.isg_reg;
+        const double zr = fma(xr, a.isg_reg, -a.mu_reg * a.isg_reg);
         accumulate_moments<D>(zr, u, acc);
     } else {
         acc[2 * D] += u;
@@ -161,7 +161,48 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_kernel(const StepArgs a
             if (a.tau) a.tau[p] = tau;
         }
     }
-    block_reduce_store<NACC, kStepThreads>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
+    block_reduce_store<NACC, kStepThreads, kAccStride>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hot-path arithmetic with every launch-uniform flag folded into constants (American decision + moments, no
+// barrier, no exercise-step array, full tile): ~24 FP64 instructions per path at degree 3.
+struct FastConsts {
+    double sgn, sgnK;       // payoff = fma(sgn, x, sgnK): put -> K - x, call -> x - K
+    double da, db;          // z_dec = fma(x, da, db)   (= (x - mu) * isg up to one rounding)
+    double ra, rb;          // z_reg = fma(x, ra, rb)
+    double disc;
+};
+
+// acc[m-1] += z^m (m = 1..2D), acc[2D+m] += z^m y (m = 0..D) with D-1 multiplies: the high powers are formed
+// inside the accumulating FMA as z^(m-D) * z^D.
+template <int D>
+__device__ __forceinline__ void accumulate_moments_fast(double z, double y, double (&acc)[3 * D + 1]) {
+    acc[2 * D] += y;
+    if (D == 0) return;
+    double p[D + 1];
+    p[0] = 1.0;
+    p[1] = z;
+#pragma unroll
+    for (int m = 2; m <= D; ++m) p[m] = p[m - 1] * z;
+#pragma unroll
+    for (int m = 1; m <= D; ++m) {
+        acc[m - 1] += p[m];
+        acc[2 * D + m] = fma(p[m], y, acc[2 * D + m]);
+        acc[D + m - 1] = fma(p[m], p[D], acc[D + m - 1]);
+    }
+}
+
+template <int D>
+__device__ __forceinline__ bool fast_path_step(const FastConsts& c, const double (&gam)[D + 1], double xd, double xr,
+                                               double& u, double (&acc)[3 * D + 1]) {
+    const double iv = fma(c.sgn, xd, c.sgnK);
+    const double zd = fma(xd, c.da, c.db);
+    const double fit = horner<D>(gam, zd);
+    const bool ex = (iv > 0.0) && (iv > fit);
+    if (ex) u = iv * c.disc;
+    accumulate_moments_fast<D>(fma(xr, c.ra, c.rb), u, acc);
+    return ex;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -244,6 +285,13 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
     }
 
     using V2 = typename Vec2<XT>::type;
+    const bool fast_ok = (a.mode == kDecide) && a.moments && !a.first_hit && !a.tau;
+    FastConsts fc;
+    fc.sgn = a.is_put ? -1.0 : 1.0;
+    fc.sgnK = a.is_put ? a.K : -a.K;
+    fc.da = a.isg_dec; fc.db = -a.mu_dec * a.isg_dec;
+    fc.ra = a.isg_reg; fc.rb = -a.mu_reg * a.isg_reg;
+    fc.disc = a.disc_dec;
     for (int i = 0; i < my_tiles; ++i) {
         const int s = i % kStages;
         if (threadIdx.x == 0 && i + kStages - 1 < my_tiles) issue(i + kStages - 1);
@@ -258,6 +306,21 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
         const V2* sxr = reinterpret_cast<const V2*>(st + kTile * sizeof(XT));
         const double2* su = reinterpret_cast<const double2*>(st + 2 * kTile * sizeof(XT));
 
+        if (fast_ok && valid == kTile) {
+#pragma unroll
+            for (int k = 0; k < kTile / 2 / kStepThreads; ++k) {
+                const int j = threadIdx.x + k * kStepThreads;
+                const V2 vd = sxd[j], vr = sxr[j];
+                double2 u = su[j];
+                bool changed = fast_path_step<D>(fc, gam, (double)vd.x, (double)vr.x, u.x, acc);
+                changed |= fast_path_step<D>(fc, gam, (double)vd.y, (double)vr.y, u.y, acc);
+                if (changed) {
+                    double2* dst = reinterpret_cast<double2*>(a.U + p0 + 2 * j);
+                    if (a.l2_hints) st_hint(dst, u, pol_keep);
+                    else *dst = u;
+                }
+            }
+        } else
 #pragma unroll
         for (int k = 0; k < kTile / 2 / kStepThreads; ++k) {
             const int j = threadIdx.x + k * kStepThreads;        // pair index inside the tile
@@ -292,7 +355,7 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
         }
         __syncthreads();                 // every warp is done with stage s before it is refilled
     }
-    block_reduce_store<NACC, kStepThreads>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
+    block_reduce_store<NACC, kStepThreads, kAccStride>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -302,34 +365,56 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
 //   phase 2 (do_solve):  thread 0 runs the k x k solve and stores gamma / diagnostics.
 //   final_price:         price = sum(U) / P.
 // Multi-GPU: phase 1, then an NCCL all-reduce of `sums`, then phase 2 as a second launch.
+constexpr int kSolveThreads = 256;
+
 template <int K>
-__global__ void __launch_bounds__(128, 1) lsm_solve_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const SolveArgs a) {
     constexpr int d = K - 1;
     constexpr int nacc = 3 * d + 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double part[kSolveThreads / 32][kAccStride];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     pdl_launch_dependents();
     pdl_wait();
     if (a.do_reduce) {
-        for (int acc = warp; acc < nacc; acc += 4) {
-            double v = 0.0;
-            for (int row = lane; row < a.n_rows; row += 32) v += a.partials[(int64_t)row * kAccStride + acc];
-            v = warp_sum(v);
-            if (lane == 0) a.sums[acc] = v;
+        // rows are 32 doubles: lane = accumulator, warp = row group; loads are coalesced and issued in batches
+        // of 8 so the latency of the (L2-resident) partials is paid a handful of times, not once per row.
+        // Summation order is fixed (row group, then rows ascending, then groups ascending): deterministic.
+        double v = 0.0;
+        int row = grp;
+        for (; row + 7 * (kSolveThreads / 32) < a.n_rows; row += 8 * (kSolveThreads / 32)) {
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = a.partials[(int64_t)(row + q * (kSolveThreads / 32)) * kAccStride + lane];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v += t[q];
         }
+        for (; row < a.n_rows; row += kSolveThreads / 32) v += a.partials[(int64_t)row * kAccStride + lane];
+        part[grp][lane] = v;
+        __syncthreads();
+        if (threadIdx.x < nacc) {
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < kSolveThreads / 32; ++q) tot += part[q][threadIdx.x];
+            a.sums[threadIdx.x] = tot;
+            part[0][threadIdx.x] = tot;
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x < nacc) part[0][threadIdx.x] = a.sums[threadIdx.x];
         __syncthreads();
     }
     if (threadIdx.x != 0) return;
     if (a.final_price) {
-        a.price[0] = a.sums[2 * d] / a.spec.n_paths;
+        a.price[0] = part[0][2 * d] / a.spec.n_paths;
         return;
     }
     if (!a.do_solve) return;
     double h[2 * d + 1], g[K];
     h[0] = a.spec.n_paths;
 #pragma unroll
-    for (int m = 1; m <= 2 * d; ++m) h[m] = a.sums[m - 1];
+    for (int m = 1; m <= 2 * d; ++m) h[m] = part[0][m - 1];
 #pragma unroll
-    for (int m = 0; m <= d; ++m) g[m] = a.sums[2 * d + m];
+    for (int m = 0; m <= d; ++m) g[m] = part[0][2 * d + m];
     SolveResult res;
     lsm_solve_t<K>(a.spec, h, g, a.y_scale, a.mu_ref, a.sigma_ref, &res);
 #pragma unroll
@@ -497,17 +582,17 @@ int step_grid_size(int dtype, int degree, int sm_count) {
 
 cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl) {
     switch (a.spec.degree) {
-        case 0: return launch_ex(lsm_solve_kernel<1>, 1, 128, 0, s, pdl, a);
-        case 1: return launch_ex(lsm_solve_kernel<2>, 1, 128, 0, s, pdl, a);
-        case 2: return launch_ex(lsm_solve_kernel<3>, 1, 128, 0, s, pdl, a);
-        case 3: return launch_ex(lsm_solve_kernel<4>, 1, 128, 0, s, pdl, a);
-        case 4: return launch_ex(lsm_solve_kernel<5>, 1, 128, 0, s, pdl, a);
-        case 5: return launch_ex(lsm_solve_kernel<6>, 1, 128, 0, s, pdl, a);
-        case 6: return launch_ex(lsm_solve_kernel<7>, 1, 128, 0, s, pdl, a);
-        case 7: return launch_ex(lsm_solve_kernel<8>, 1, 128, 0, s, pdl, a);
-        case 8: return launch_ex(lsm_solve_kernel<9>, 1, 128, 0, s, pdl, a);
-        case 9: return launch_ex(lsm_solve_kernel<10>, 1, 128, 0, s, pdl, a);
-        case 10: return launch_ex(lsm_solve_kernel<11>, 1, 128, 0, s, pdl, a);
+        case 0: return launch_ex(lsm_solve_kernel<1>, 1, kSolveThreads, 0, s, pdl, a);
+        case 1: return launch_ex(lsm_solve_kernel<2>, 1, kSolveThreads, 0, s, pdl, a);
+        case 2: return launch_ex(lsm_solve_kernel<3>, 1, kSolveThreads, 0, s, pdl, a);
+        case 3: return launch_ex(lsm_solve_kernel<4>, 1, kSolveThreads, 0, s, pdl, a);
+        case 4: return launch_ex(lsm_solve_kernel<5>, 1, kSolveThreads, 0, s, pdl, a);
+        case 5: return launch_ex(lsm_solve_kernel<6>, 1, kSolveThreads, 0, s, pdl, a);
+        case 6: return launch_ex(lsm_solve_kernel<7>, 1, kSolveThreads, 0, s, pdl, a);
+        case 7: return launch_ex(lsm_solve_kernel<8>, 1, kSolveThreads, 0, s, pdl, a);
+        case 8: return launch_ex(lsm_solve_kernel<9>, 1, kSolveThreads, 0, s, pdl, a);
+        case 9: return launch_ex(lsm_solve_kernel<10>, 1, kSolveThreads, 0, s, pdl, a);
+        case 10: return launch_ex(lsm_solve_kernel<11>, 1, kSolveThreads, 0, s, pdl, a);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

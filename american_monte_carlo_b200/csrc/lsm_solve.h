@@ -215,6 +215,9 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
         AMC_UNROLL
         for (int j = 0; j < K; ++j) L[i][j] = 0.0;
     }
+    double Linv[K];               // 1 / L[j][j]: one division per pivot, multiplications everywhere else
+    AMC_UNROLL
+    for (int i = 0; i < K; ++i) Linv[i] = 0.0;
     int kint = K;
     const double pivot_tol = 2e-14;
     AMC_UNROLL
@@ -227,13 +230,15 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
                 kint = j;
             } else {
                 const double ljj = sqrt(djj);
+                const double inv = 1.0 / ljj;
                 L[j][j] = ljj;
+                Linv[j] = inv;
                 AMC_UNROLL
                 for (int i = j + 1; i < K; ++i) {
                     double v = Hn[i + j];
                     AMC_UNROLL
                     for (int c = 0; c < j; ++c) v -= L[i][c] * L[j][c];
-                    L[i][j] = v / ljj;
+                    L[i][j] = v * inv;
                 }
             }
         }
@@ -248,7 +253,7 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
         double v = b[i];
         AMC_UNROLL
         for (int c = 0; c < i; ++c) v -= L[i][c] * w[c];
-        w[i] = (i < kint) ? v / L[i][i] : 0.0;
+        w[i] = (i < kint) ? v * Linv[i] : 0.0;
     }
 
     // change of basis for the user's polynomials: u = a + b z
@@ -328,6 +333,9 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
             for (int j = 0; j < K; ++j) {
                 ok = ok && (B[j][j] != 0.0);
                 Bi[j][j] = 1.0 / B[j][j];
+            }
+            AMC_UNROLL
+            for (int j = 0; j < K; ++j) {
                 AMC_UNROLL
                 for (int i = K - 1; i >= 0; --i) {
                     if (i < j) {
@@ -335,7 +343,7 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
                         AMC_UNROLL
                         for (int l = 0; l < K; ++l)
                             if (l > i && l <= j) v += B[i][l] * Bi[l][j];
-                        Bi[i][j] = -v / B[i][i];
+                        Bi[i][j] = -v * Bi[i][i];
                     }
                 }
                 AMC_UNROLL
@@ -408,7 +416,7 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
             AMC_UNROLL
             for (int c = 0; c < K; ++c)
                 if (c > i && c < kint) v -= L[c][i] * out->gamma[c];
-            out->gamma[i] = v / L[i][i];
+            out->gamma[i] = v * Linv[i];
         }
     }
 }
