@@ -138,7 +138,7 @@ def cpu_oracle_rate(wl, sample_paths, repeats=1):
                 price=best[3], seconds=best[0])
 
 
-def run_reference(args, wl, rank):
+def run_reference(args, wl, rank, emit):
     """--impl reference: the reference's own CPU algorithm (oracle port; /root/reference is absent on the box)."""
     if rank != 0:
         return
@@ -153,7 +153,7 @@ def run_reference(args, wl, rank):
     value = sample * wl["n"] / mean_s
     cb = dict(rate, value=value)
     cb.pop("seconds", None)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "LSM path-steps/sec (path simulation + backward induction)", "value": value,
         "unit": "path-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -162,6 +162,19 @@ def run_reference(args, wl, rank):
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def claim_stdout():
+    """Route everything libraries print to stdout (e.g. NCCL's version banner) to stderr; return a writer for the
+    one JSON line the contract allows on stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text):
+        sys.stdout.flush()
+        os.write(real, (text + "\n").encode())
+    return emit
 
 
 def main():
@@ -181,7 +194,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        run_reference(args, wl, rank, claim_stdout())
         return
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -190,6 +203,7 @@ def main():
                    "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 500)] + sys.argv
             sys.exit(subprocess.call(cmd))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    emit = claim_stdout()
 
     import numpy as np
     import torch
@@ -376,7 +390,7 @@ def main():
         cb.pop("seconds", None)
         line["cpu_baseline"] = cb
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
