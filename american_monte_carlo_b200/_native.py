@@ -44,6 +44,7 @@ PROTOTYPES = {
     "amc_comm_unique_id": (C.c_int, [C.c_char_p]),
     "amc_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "amc_comm_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
+    "amc_comm_transport": (C.c_int, [C.c_void_p, c_int_p]),
     "amc_comm_allreduce_host": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "amc_paths_generate": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int64,
                                      C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),

@@ -63,6 +63,13 @@ class Context:
         N.check(N.lib().amc_comm_init(self.handle, int(world_size), int(rank), C.c_char_p(unique_id)))
         self.world_size, self.rank = int(world_size), int(rank)
 
+    @property
+    def transport(self) -> str:
+        """How the per-step all-reduce travels: 'none' (one GPU), 'nccl', or 'p2p' (fused, NVLink peer memory)."""
+        t = C.c_int()
+        N.check(N.lib().amc_comm_transport(self.handle, C.byref(t)))
+        return {0: "none", 1: "nccl", 2: "p2p"}[t.value]
+
     def allreduce_host(self, arr: np.ndarray) -> np.ndarray:
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         N.check(N.lib().amc_comm_allreduce_host(self.handle, arr.ctypes.data_as(N.c_double_p), arr.size))

@@ -97,6 +97,13 @@ struct amc_ctx {
     size_t total_mem = 0;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
+    // fused all-reduce over NVLink peer memory (PeerArgs in kernels.h): own mailbox + the peers' mailboxes mapped
+    // through CUDA IPC.  transport: 0 = single GPU, 1 = NCCL all-reduce between two solve launches, 2 = peer memory
+    int transport = 0;
+    void* mailbox = nullptr;
+    void* peer_mailbox[kPeerMax] = {};
+    int* peer_err = nullptr;
+    uint32_t peer_seq = 0;
     // grow-only scratch (one pricing call at a time per context)
     DevBuf U, tau, first_hit, partials, sums, diag, stage, misc;
     std::vector<cudaEvent_t> events;
@@ -165,6 +172,10 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
     if (!c) return AMC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int q = 0; q < kPeerMax; ++q)
+        if (c->peer_mailbox[q] && q != c->rank) cudaIpcCloseMemHandle(c->peer_mailbox[q]);
+    if (c->mailbox) cudaFree(c->mailbox);
+    if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
     DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc};
     for (DevBuf* b : bufs)
@@ -203,6 +214,56 @@ extern "C" int amc_comm_unique_id(char id[128]) {
     return AMC_OK;
 }
 
+// Map every rank's mailbox into this process.  The 64-byte IPC handles travel through one NCCL all-gather; every
+// rank then reports whether it could open all of them and the minimum over ranks decides (so either all ranks use
+// peer memory or none does).
+static int peer_setup(amc_ctx* c) {
+    const int W = c->world;
+    if (W > kPeerMax) return fail(AMC_ERR_NCCL, "peer-memory all-reduce supports up to %d ranks", kPeerMax);
+    const size_t box_bytes = (size_t)kPeerRing * W * kAccStride * sizeof(uint4);
+    CU(cudaMalloc(&c->mailbox, box_bytes));
+    CU(cudaMalloc((void**)&c->peer_err, 256));
+    CU(cudaMemsetAsync(c->mailbox, 0, box_bytes, c->stream));
+    CU(cudaMemsetAsync(c->peer_err, 0, 256, c->stream));
+    CU(cudaStreamSynchronize(c->stream));              // zeroed before any peer can learn the handle
+    cudaIpcMemHandle_t mine;
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) { ok = 0; memset(&mine, 0, sizeof(mine)); cudaGetLastError(); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    int rc = ensure(c->misc, 64 * (size_t)(W + 1) + 64);
+    if (rc) return rc;
+    char* send = (char*)c->misc.p;
+    char* recv = send + 64;
+    CU(cudaMemcpyAsync(send, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(send, recv, 64, ncclChar, c->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    CU(cudaMemcpyAsync(all.data(), recv, 64 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    char why[160] = "";
+    for (int q = 0; q < W && ok; ++q) {
+        if (q == c->rank) { c->peer_mailbox[q] = c->mailbox; continue; }
+        cudaError_t e = cudaIpcOpenMemHandle(&c->peer_mailbox[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            snprintf(why, sizeof(why), "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+            c->peer_mailbox[q] = nullptr;
+            cudaGetLastError();
+            ok = 0;
+        }
+    }
+    // agreement: sum of ok flags must equal W
+    double flag = ok ? 1.0 : 0.0;
+    double* fdev = (double*)c->misc.p;
+    CU(cudaMemcpyAsync(fdev, &flag, 8, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(fdev, fdev, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+    CU(cudaMemcpyAsync(&flag, fdev, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if ((int)(flag + 0.5) != W)
+        return fail(AMC_ERR_NCCL, "%d of %d ranks could map all mailboxes%s%s", (int)(flag + 0.5), W, why[0] ? "; " : "", why);
+    c->transport = 2;
+    c->peer_seq = 0;
+    return AMC_OK;
+}
+
 extern "C" int amc_comm_init(amc_ctx* c, int world_size, int rank, const char id[128]) {
     if (!c) return fail(AMC_ERR_VALUE, "null context");
     if (world_size < 1 || rank < 0 || rank >= world_size)
@@ -217,6 +278,19 @@ extern "C" int amc_comm_init(amc_ctx* c, int world_size, int rank, const char id
     NC(g_nccl.CommInitRank(&c->comm, world_size, uid, rank));
     c->world = world_size;
     c->rank = rank;
+    c->transport = 1;
+    // AMC_ALLREDUCE = p2p (must work) | nccl (do not try) | unset: peer memory when every rank can map every mailbox
+    const char* mode = getenv("AMC_ALLREDUCE");
+    if (mode && mode[0] == 'n') return AMC_OK;
+    rc = peer_setup(c);
+    if (rc != AMC_OK && mode && mode[0] == 'p') return rc;
+    if (rc != AMC_OK) fprintf(stderr, "libamc: rank %d: peer-memory all-reduce unavailable (%s); using NCCL\n", rank, g_err);
+    return AMC_OK;
+}
+
+extern "C" int amc_comm_transport(amc_ctx* c, int* transport) {
+    if (!c || !transport) return fail(AMC_ERR_VALUE, "null argument");
+    *transport = c->transport;
     return AMC_OK;
 }
 
@@ -607,7 +681,7 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     // programmatic dependent launch along the K3 -> K4 -> K3 chain (single GPU, not while profiling: the
     // per-launch events and the NCCL kernels are ordinary stream dependencies)
     static const int opt_pdl = getenv("AMC_PDL") ? atoi(getenv("AMC_PDL")) : 1;
-    const bool pdl = opt_pdl && !profile && c->world == 1;
+    const bool pdl = opt_pdl && !profile && (c->world == 1 || c->transport == 2);
     EventPool pool{c};
     cudaEvent_t ev_start, ev_stop;
     if ((rc = pool.get(&ev_start)) || (rc = pool.get(&ev_stop))) return rc;
@@ -682,10 +756,18 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         s.price = dg + off_price;
         int r2;
         if ((r2 = bracket(solve_ev))) return r2;
-        if (c->world == 1) {
+        if (c->world == 1 || c->transport == 2) {
             s.do_reduce = 1;
             s.do_solve = final_price ? 0 : 1;
             s.final_price = final_price ? 1 : 0;
+            if (c->world > 1) {
+                for (int q = 0; q < c->world; ++q) s.peer.mailbox[q] = (uint4*)c->peer_mailbox[q];
+                s.peer.world = c->world;
+                s.peer.rank = c->rank;
+                s.peer.seq = ++c->peer_seq;
+                if (s.peer.seq == 0) s.peer.seq = ++c->peer_seq;      // 0 is the "empty cell" value
+                s.peer.err = c->peer_err;
+            }
             CU(launch_solve(s, c->stream, pdl));
             ++n_solve;
         } else {
@@ -730,7 +812,13 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         CU(cudaMemcpyAsync(exercise_step_out, tau, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (cashflow0_out && P > 0)
         CU(cudaMemcpyAsync(cashflow0_out, c->U.p, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+    int peer_err_h = 0;
+    if (c->transport == 2) CU(cudaMemcpyAsync(&peer_err_h, c->peer_err, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (peer_err_h) {
+        cudaMemsetAsync(c->peer_err, 0, 4, c->stream);
+        return fail(AMC_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not reach the same step of the sweep");
+    }
     *price = price_h[0];
 
     if (steps) {

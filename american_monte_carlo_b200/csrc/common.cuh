@@ -158,3 +158,26 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 }  // namespace amc
+
+// ---- LL cells for the peer-memory all-reduce (see PeerArgs in kernels.h) ---------------------------------------
+// A cell is 16 bytes {data_lo, flag, data_hi, flag}: every 8-byte half carries its own flag, so the protocol only
+// needs 8-byte store atomicity (what NCCL's LL protocol relies on); volatile accesses go to L2 / the peer, never L1.
+namespace amc {
+__device__ __forceinline__ void st_ll(uint4* cell, double v, uint32_t flag) {
+    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(lo), "r"(flag), "r"(hi), "r"(flag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const uint4* cell, uint32_t flag, double& v) {
+    uint32_t lo, f0, hi, f1;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(cell)
+                 : "memory");
+    v = __hiloint2double((int)hi, (int)lo);
+    return f0 == flag && f1 == flag;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+}  // namespace amc

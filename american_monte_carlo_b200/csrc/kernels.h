@@ -40,6 +40,21 @@ struct StepArgs {
     double mu_reg, isg_reg;    // affine map of column t_dec-1
 };
 
+// One-shot all-reduce of the moment sums over NVLink peer memory, fused into the solve kernel (multi-GPU).
+// Every rank owns a mailbox of kPeerRing x world x kAccStride 16-byte cells {lo32, seq, hi32, seq}; the solve block of
+// rank r stores its reduced sums straight into slot [seq % kPeerRing][r] of EVERY rank's mailbox (peer stores through
+// NVSwitch), then spins on its own mailbox until all `world` rows carry the current sequence number and adds them in
+// rank order -- the same bits on every rank, no NCCL kernel, no extra launch, no fence (the flag travels with the data,
+// as in NCCL's LL protocol).
+constexpr int kPeerMax = 8;
+constexpr int kPeerRing = 4;
+struct PeerArgs {
+    uint4* mailbox[kPeerMax] = {};  // mailbox[q] = rank q's mailbox mapped into this process (cudaIpc); [rank] = own
+    int world = 0, rank = 0;        // world <= 1: no exchange
+    uint32_t seq = 0;               // sequence number of this all-reduce (never 0), same on every rank
+    int* err = nullptr;             // device flag: set to 1 if a peer did not show up in time
+};
+
 struct SolveArgs {
     const double* partials;    // [n_rows][kAccStride] (null: skip the reduction, sums already hold totals)
     int n_rows;
@@ -55,6 +70,7 @@ struct SolveArgs {
     double* mean_std;          // [2]
     int* rank;                 // [1]
     double* price;             // [1] (final_price)
+    PeerArgs peer;
 };
 
 int step_grid_size(int dtype, int degree, int sm_count);

@@ -403,6 +403,39 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
         if (threadIdx.x < nacc) part[0][threadIdx.x] = a.sums[threadIdx.x];
         __syncthreads();
     }
+    if (a.peer.world > 1) {
+        // fused all-reduce over peer memory: push this rank's sums into everybody's mailbox, then gather
+        const int W = a.peer.world;
+        const uint32_t seq = a.peer.seq;
+        const int slot = (int)(seq % kPeerRing);
+        for (int idx = threadIdx.x; idx < W * nacc; idx += kSolveThreads) {
+            const int q = idx / nacc, i = idx - q * nacc;
+            st_ll(a.peer.mailbox[q] + ((slot * W + a.peer.rank) * kAccStride + i), part[0][i], seq);
+        }
+        double tot = 0.0;
+        if (threadIdx.x < nacc) {
+            const uint4* mine = a.peer.mailbox[a.peer.rank] + (slot * W) * kAccStride + threadIdx.x;
+            const uint64_t t0 = global_timer_ns();
+            for (int q = 0; q < W; ++q) {                  // rank order: identical bits on every rank
+                double v;
+                int spins = 0;
+                while (!ld_ll(mine + q * kAccStride, seq, v)) {
+                    if (((++spins) & 1023) == 0 && global_timer_ns() - t0 > 4000000000ull) {   // 4 s: a peer is gone
+                        *a.peer.err = 1;
+                        v = 0.0;
+                        break;
+                    }
+                }
+                tot += v;
+            }
+        }
+        __syncthreads();                                   // every thread has read part[0][*] for its pushes
+        if (threadIdx.x < nacc) {
+            part[0][threadIdx.x] = tot;
+            a.sums[threadIdx.x] = tot;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x != 0) return;
     if (a.final_price) {
         a.price[0] = part[0][2 * d] / a.spec.n_paths;

@@ -361,7 +361,7 @@ def main():
         "dtype": "f64" if did == N.F64 else "f64 sums over f32 paths", "data": data,
         "config": {"workload": args.workload, "description": wl["label"], "contract": "American put " + json.dumps(LS_PUT),
                    "paths_per_gpu": P_local, "paths_total": P_global, "time_steps": n, "basis": wl["basis"],
-                   "degree": wl["degree"], "path_dtype": wl["dtype"], "rng": wl["rng"],
+                   "degree": wl["degree"], "path_dtype": wl["dtype"], "rng": wl["rng"], "allreduce": ctx.transport,
                    "l2": "inputs larger than L2 (path matrix %.1f GB per GPU re-streamed every step)" % (P_local * (n + 1) * bS / 1e9)},
         "e2e": {"value": e2e_value, "unit": "path-steps/s",
                 "h2d_bytes_per_step": (P_local * n * 8 if wl["rng"] == "normals" else 0) * world,

@@ -63,6 +63,10 @@ int amc_ctx_device_info(amc_ctx* ctx, int* sm_count, int* cc_major, int* cc_mino
 int amc_comm_unique_id(char id[128]);
 int amc_comm_init(amc_ctx* ctx, int world_size, int rank, const char id[128]);
 int amc_comm_info(amc_ctx* ctx, int* world_size, int* rank);
+/* how the per-step all-reduce of the moment sums travels: 0 = single GPU (none), 1 = ncclAllReduce between two solve
+ * launches, 2 = fused into the solve kernel over NVLink peer memory (CUDA-IPC-mapped mailboxes; the default when
+ * every rank can map every peer; AMC_ALLREDUCE=nccl|p2p forces one) */
+int amc_comm_transport(amc_ctx* ctx, int* transport);
 /* sum-all-reduce `n` doubles in place on a host buffer (tiny; used for column statistics and tests) */
 int amc_comm_allreduce_host(amc_ctx* ctx, double* buf, int n);
 

@@ -22,7 +22,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     rank, world = dist.get_rank(), dist.get_world_size()
     ctx = init_distributed()
-    out = {}
+    out = {"transport": ctx.transport}
 
     # (1) injected reference normals, sharded by rows: must equal the oracle with zero flipped decisions
     S0, K, r, sigma, T, n, P = 36.0, 40.0, 0.06, 0.2, 1.0, 50, 100_000

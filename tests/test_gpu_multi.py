@@ -10,21 +10,29 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_workers(n):
+def run_workers(n, allreduce=None):
+    env = dict(os.environ)
+    env.pop("AMC_ALLREDUCE", None)
+    if allreduce:
+        env["AMC_ALLREDUCE"] = allreduce
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", "29653", os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
     return json.loads(line[len("MGPU_RESULT "):])
 
 
-def test_sharded_sweep_equals_single_gpu_and_oracle(libamc_path):
+@pytest.mark.parametrize("allreduce", ["p2p", "nccl"])
+def test_sharded_sweep_equals_single_gpu_and_oracle(libamc_path, allreduce):
+    """p2p: the all-reduce fused into the solve kernel over NVLink peer memory (the default transport);
+    nccl: ncclAllReduce between two solve launches (kept as the baseline it is measured against)."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    out = run_workers(min(n, 8) if n in (2, 4, 8) else 2)
+    out = run_workers(min(n, 8) if n in (2, 4, 8) else 2, allreduce)
+    assert out["transport"] == allreduce
     inj = out["injected"]
     assert inj["flips"] == 0 and inj["ranks_equal"]
     assert abs(inj["price"] - inj["oracle"]) <= 1e-10 * inj["oracle"]
