@@ -4,11 +4,11 @@ Host-side mirror of /root/reference/american_monte_carlo.py:72-197 over the C AB
 Importing the package does not need a GPU; the first call that computes anything does, and raises without one.
 """
 from .api import (Context, ContinuationValues, DevicePaths, LsmResult, default_context, generate_asset_paths,  # noqa: F401
-                  get_basis_polynomials, intrinsic_value, lsm_price, lsmc_option_pricing, paths_from_host,
+                  get_basis_polynomials, intrinsic_value, lsm_price, lsm_price_batch, lsmc_option_pricing, paths_from_host,
                   paths_from_normals, precompute_barrier_hit_matrix, regression_estimate, set_default_context,
                   shard_range)
 
 __all__ = ["Context", "ContinuationValues", "DevicePaths", "LsmResult", "default_context", "generate_asset_paths",
-           "get_basis_polynomials", "intrinsic_value", "lsm_price", "lsmc_option_pricing", "paths_from_host",
+           "get_basis_polynomials", "intrinsic_value", "lsm_price", "lsm_price_batch", "lsmc_option_pricing", "paths_from_host",
            "paths_from_normals", "precompute_barrier_hit_matrix", "regression_estimate", "set_default_context",
            "shard_range"]

@@ -20,7 +20,7 @@ class LsmSpec(C.Structure):
     _fields_ = [("K", C.c_double), ("r", C.c_double), ("dt", C.c_double), ("barrier", C.c_double),
                 ("scaling_factor", C.c_double), ("is_put", C.c_int), ("is_american", C.c_int), ("basis", C.c_int),
                 ("degree", C.c_int), ("scaling", C.c_int), ("want_regression", C.c_int),
-                ("want_exercise_steps", C.c_int), ("want_svd", C.c_int)]
+                ("want_exercise_steps", C.c_int), ("want_svd", C.c_int), ("state_f32", C.c_int)]
 
 
 class LsmSteps(C.Structure):
@@ -61,6 +61,8 @@ PROTOTYPES = {
     "amc_paths_column_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amc_lsm_price": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LsmSpec), c_double_p, C.POINTER(LsmSteps),
                                 C.c_void_p, C.c_void_p, C.POINTER(LsmTiming), C.c_int]),
+    "amc_lsm_price_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LsmSpec), C.c_int, c_double_p, C.c_void_p,
+                                      C.POINTER(LsmTiming), C.c_int]),
     "amc_continuation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "amc_intrinsic_value": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]),
     "amc_regression_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,

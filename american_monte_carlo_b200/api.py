@@ -282,7 +282,8 @@ def _as_device_paths(paths, ctx):
 
 def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="European", basis_type="Chebyshev",
               degree=4, scaling=False, scaling_factor=2, *, want_regression=None, want_exercise_steps=False,
-              want_cashflows=False, want_svd=False, profile=False, ctx: Context | None = None) -> LsmResult:
+              want_cashflows=False, want_svd=False, state_dtype="float64", profile=False,
+              ctx: Context | None = None) -> LsmResult:
     """One backward sweep (amc.py:139-197) with all diagnostics.  `lsmc_option_pricing` is the reference-shaped wrapper."""
     ctx = ctx or default_context()
     dp, temporary = _as_device_paths(paths, ctx)
@@ -298,7 +299,8 @@ def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="E
                          scaling_factor=float(scaling_factor), is_put=int(option_type == "Put"),    # amc.py:86
                          is_american=int(american), basis=N.BASIS_ID.get(basis_type, 0), degree=int(degree),
                          scaling=int(bool(scaling)), want_regression=int(bool(want_regression)),
-                         want_exercise_steps=int(bool(want_exercise_steps)), want_svd=int(bool(want_svd)))
+                         want_exercise_steps=int(bool(want_exercise_steps)), want_svd=int(bool(want_svd)),
+                         state_f32=int(_dtype_id(state_dtype) == N.F32))
         rows = n + 1
         st = dict(gamma=np.zeros((rows, N.AMC_MAX_K)), beta=np.zeros((rows, N.AMC_MAX_K)),
                   sv=np.zeros((rows, N.AMC_MAX_K)), mean_x=np.zeros(rows), std_x=np.zeros(rows),
@@ -317,6 +319,50 @@ def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="E
                   step_launches=timing.step_launches, solve_launches=timing.solve_launches,
                   other_launches=timing.other_launches)
         return LsmResult(np.float64(price.value), n, int(degree), st, tm, ex, cf)
+    finally:
+        if temporary:
+            dp.free()
+
+
+def lsm_price_batch(paths, contracts, r, dt, barrier_level=None, basis_type="Chebyshev", degree=4, scaling=False,
+                    scaling_factor=2, *, want_gamma=False, state_dtype="float64", profile=False,
+                    ctx: Context | None = None):
+    """Price several contracts on ONE path set in the same launches (include/amc.h: amc_lsm_price_batch).
+
+    `contracts` is a sequence of (K, option_type, exercise_type) -- the arguments of amc.py:180 that may vary inside a
+    batch; r, dt, barrier, basis and scaling are shared.  Returns an ndarray of prices (and, with want_gamma, the
+    per-contract continuation polynomials [n_contracts, n_time_steps+1, AMC_MAX_K]).  Each price equals what
+    `lsmc_option_pricing` returns for that contract alone, to rounding.  The reference has no batched call: its sweeps
+    (plots.py:100-107) loop over contracts in Python, re-simulating and re-pricing each one.
+    """
+    ctx = ctx or default_context()
+    dp, temporary = _as_device_paths(paths, ctx)
+    try:
+        contracts = list(contracts)
+        if not contracts:
+            return np.zeros(0)
+        if dp.n_time_steps >= 1:
+            _check_basis(basis_type)
+        specs = (N.LsmSpec * len(contracts))()
+        for i, (K, option_type, exercise_type) in enumerate(contracts):
+            specs[i] = N.LsmSpec(K=float(K), r=float(r), dt=float(dt),
+                                 barrier=float("nan") if barrier_level is None else float(barrier_level),
+                                 scaling_factor=float(scaling_factor), is_put=int(option_type == "Put"),
+                                 is_american=int(exercise_type == "American"), basis=N.BASIS_ID.get(basis_type, 0),
+                                 degree=int(degree), scaling=int(bool(scaling)), want_regression=0,
+                                 want_exercise_steps=0, want_svd=0, state_f32=int(_dtype_id(state_dtype) == N.F32))
+        prices = np.zeros(len(contracts))
+        gamma = np.zeros((len(contracts), dp.n_time_steps + 1, N.AMC_MAX_K)) if want_gamma else None
+        timing = N.LsmTiming()
+        N.check(N.lib().amc_lsm_price_batch(ctx.handle, dp.handle, specs, len(contracts),
+                                            prices.ctypes.data_as(N.c_double_p),
+                                            gamma.ctypes.data if gamma is not None else None, C.byref(timing),
+                                            int(bool(profile))))
+        prices_timing = dict(total_ms=timing.total_ms, step_kernel_ms=timing.step_kernel_ms,
+                             solve_kernel_ms=timing.solve_kernel_ms, step_launches=timing.step_launches,
+                             solve_launches=timing.solve_launches, other_launches=timing.other_launches)
+        lsm_price_batch.last_timing = prices_timing
+        return (prices, gamma) if want_gamma else prices
     finally:
         if temporary:
             dp.free()

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libamc.so")
-SOURCES = ["api.cu", "lsm_kernels.cu", "pathgen.cu"]
-HEADERS = ["common.cuh", "kernels.h", "lsm_solve.h", "philox.cuh", os.path.join(ROOT, "include", "amc.h")]
+SOURCES = ["lsm_step_f32.cu", "lsm_step_f64.cu", "lsm_step_f32s.cu", "lsm_kernels.cu", "api.cu", "pathgen.cu"]
+HEADERS = ["common.cuh", "kernels.h", "lsm_solve.h", "philox.cuh", "lsm_step.cuh", "launch.cuh", os.path.join(ROOT, "include", "amc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -39,12 +39,29 @@ def build(force=False, verbose=False):
     """Compile every CUDA source of the package for sm_100a.  Returns the path of libamc.so."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-ldl"]
+    # one object per source, compiled concurrently, then one link
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + compile_flags + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        if verbose:
+            sys.stderr.write(proc.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + objs + ["-ldl"]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     return LIB
 
 

@@ -105,9 +105,9 @@ struct amc_ctx {
     int* peer_err = nullptr;
     uint32_t peer_seq = 0;
     // grow-only scratch (one pricing call at a time per context)
-    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc;
+    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab;
     std::vector<cudaEvent_t> events;
-    int grid_cache[2][AMC_MAX_K];
+    int grid_cache[3][AMC_MAX_K];
     // freed path matrices are kept for reuse (all work is ordered on one stream, so a recycled buffer is safe):
     // a pricing loop then never pays cudaMalloc/cudaFree (both synchronise the device) for multi-GB matrices
     std::vector<DevBuf> path_pool;
@@ -162,7 +162,7 @@ extern "C" int amc_ctx_create(int device, void* stream, amc_ctx** out) {
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
         for (int j = 0; j < AMC_MAX_K; ++j) c->grid_cache[i][j] = 0;
     *out = c;
     return AMC_OK;
@@ -177,7 +177,7 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
     if (c->mailbox) cudaFree(c->mailbox);
     if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
-    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc};
+    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc, &c->batch_tab};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf& b : c->path_pool)
@@ -609,9 +609,9 @@ static int check_spec(const amc_lsm_spec* s) {
     return AMC_OK;
 }
 
-static int step_grid(amc_ctx* c, int dtype, int degree, int64_t n_paths) {
-    int& g = c->grid_cache[dtype][degree];
-    if (g == 0) g = step_grid_size(dtype, degree, c->sm_count);
+static int step_grid(amc_ctx* c, int dtype, int state_f32, int degree, int64_t n_paths) {
+    int& g = c->grid_cache[state_f32 ? 2 : dtype][degree];
+    if (g == 0) g = step_grid_size(dtype, state_f32, degree, c->sm_count);
     // small path sets: no more blocks than there are tiles of 1024 paths to hand out
     int64_t need = (n_paths + 1023) / 1024;
     if (need < 1) need = 1;
@@ -632,43 +632,65 @@ struct EventPool {
     }
 };
 
-extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* spec, double* price,
-                             amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out,
-                             amc_lsm_timing* timing, int profile) {
-    if (!c || !p || !price) return fail(AMC_ERR_VALUE, "amc_lsm_price: null argument");
-    if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_lsm_price: path set belongs to another context");
-    int rc = check_spec(spec);
-    if (rc) return rc;
-    if (exercise_step_out && !spec->want_exercise_steps)
-        return fail(AMC_ERR_VALUE, "exercise_step_out needs spec.want_exercise_steps");
+// One backward sweep for `C` contracts on one path set.  C == 1: the single-contract entry point with all its
+// diagnostics.  C > 1 (amc_lsm_price_batch): the contracts share r, dt, basis, degree, scaling and barrier and differ
+// in strike / payoff side / exercise style; every launch carries all of them (grid.y = contract), so the columns are
+// read from HBM once per step for the whole batch and the per-step launch chain is paid once.
+static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, int C, double* price,
+                     amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out, double* gamma_batch_out,
+                     amc_lsm_timing* timing, int profile) {
+    const amc_lsm_spec* spec = specs;
+    int rc;
     CU(cudaSetDevice(c->device));
 
     const int n = p->n_steps, D = spec->degree, dtype = p->dtype;
     const int64_t P = p->n_local;
     const double Pg = (double)p->n_global;
-    const bool american = spec->is_american != 0;
+    bool american = false;
+    for (int i = 0; i < C; ++i) american = american || specs[i].is_american != 0;
     const bool regress = (american || spec->want_regression) && n >= 1;
     const bool barrier = !isnan(spec->barrier);
-    const int grid = step_grid(c, dtype, D, P);
+    const int sf32 = spec->state_f32 ? 1 : 0;
+    const size_t bU = sf32 ? 4 : 8;
+    int grid = step_grid(c, dtype, sf32, D, P);
+    if (C > 1) {                                      // all contracts' blocks co-resident: split the grid among them
+        grid = grid / C;                              // floor: one block too many per contract would add a whole wave
+        if (grid < 1) grid = 1;
+    }
     const double rdt = spec->r * spec->dt;
+    const bool exchange = c->world > 1 && C == 1;     // batches are sharded by contract: no data-path collective
 
     // scratch
     const int64_t ldp = padded_len(P > 0 ? P : 1);
-    if ((rc = ensure(c->U, (size_t)ldp * 8))) return rc;
+    if ((rc = ensure(c->U, (size_t)ldp * bU * C))) return rc;
     if (spec->want_exercise_steps && (rc = ensure(c->tau, (size_t)ldp * 4))) return rc;
     if (barrier && (rc = ensure(c->first_hit, (size_t)ldp * 4))) return rc;
-    if ((rc = ensure(c->partials, (size_t)grid * kAccStride * 8))) return rc;
-    if ((rc = ensure(c->sums, kAccStride * 8))) return rc;
-    // diagnostics block: gamma | beta | sv | mean_std | price | rank
+    if ((rc = ensure(c->partials, (size_t)grid * kAccStride * 8 * C))) return rc;
+    if ((rc = ensure(c->sums, kAccStride * 8 * (size_t)C))) return rc;
+    // diagnostics block: gamma (one [n+1][kMaxK] table per contract) | beta | sv | mean_std | price | rank
     const size_t nrow = (size_t)(n + 1);
-    const size_t off_gamma = 0, off_beta = nrow * kMaxK, off_sv = 2 * nrow * kMaxK, off_ms = 3 * nrow * kMaxK;
-    const size_t off_price = off_ms + 2 * nrow, off_rank = off_price + 2;    // rank stored as int32 after doubles
+    const size_t off_gamma = 0, off_beta = (size_t)C * nrow * kMaxK, off_sv = off_beta + nrow * kMaxK;
+    const size_t off_ms = off_sv + nrow * kMaxK;
+    const size_t off_price = off_ms + 2 * nrow, off_rank = off_price + (size_t)C + 1;   // rank: int32 after the doubles
     const size_t diag_bytes = off_rank * 8 + nrow * 4;
     if ((rc = ensure(c->diag, diag_bytes))) return rc;
     double* dg = (double*)c->diag.p;
     int* drank = (int*)(dg + off_rank);
     CU(cudaMemsetAsync(c->diag.p, 0, diag_bytes, c->stream));
-    CU(cudaMemsetAsync(c->sums.p, 0, kAccStride * 8, c->stream));
+    CU(cudaMemsetAsync(c->sums.p, 0, kAccStride * 8 * (size_t)C, c->stream));
+    BatchContract* tab = nullptr;
+    std::vector<BatchContract> tab_h;
+    if (C > 1) {
+        if ((rc = ensure(c->batch_tab, sizeof(BatchContract) * (size_t)C))) return rc;
+        tab = (BatchContract*)c->batch_tab.p;
+        tab_h.resize(C);
+        for (int i = 0; i < C; ++i) {
+            tab_h[i].K = specs[i].K;
+            tab_h[i].is_put = specs[i].is_put;
+            tab_h[i].is_american = specs[i].is_american;
+        }
+        CU(cudaMemcpyAsync(tab, tab_h.data(), sizeof(BatchContract) * (size_t)C, cudaMemcpyHostToDevice, c->stream));
+    }
 
     int32_t* tau = spec->want_exercise_steps ? (int32_t*)c->tau.p : nullptr;
     int32_t* fh = barrier ? (int32_t*)c->first_hit.p : nullptr;
@@ -681,7 +703,7 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     // programmatic dependent launch along the K3 -> K4 -> K3 chain (single GPU, not while profiling: the
     // per-launch events and the NCCL kernels are ordinary stream dependencies)
     static const int opt_pdl = getenv("AMC_PDL") ? atoi(getenv("AMC_PDL")) : 1;
-    const bool pdl = opt_pdl && !profile && (c->world == 1 || c->transport == 2);
+    const bool pdl = opt_pdl && !profile && (!exchange || c->transport == 2);
     EventPool pool{c};
     cudaEvent_t ev_start, ev_stop;
     if ((rc = pool.get(&ev_start)) || (rc = pool.get(&ev_stop))) return rc;
@@ -711,7 +733,7 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         StepArgs a;
         a.x_dec = (mode != kObserve) ? column(p, t) : nullptr;
         a.x_reg = moments ? column(p, t - 1) : nullptr;
-        a.U = (double*)c->U.p;
+        a.U = c->U.p;
         a.tau = tau;
         a.first_hit = fh;
         a.coef = dg + off_gamma + (size_t)t * kMaxK;
@@ -729,9 +751,12 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         a.isg_dec = 1.0 / p->sigma[t];
         a.mu_reg = moments ? p->mu[t - 1] : 0.0;
         a.isg_reg = moments ? 1.0 / p->sigma[t - 1] : 1.0;
+        a.batch = tab;
+        a.u_stride = ldp;
+        a.coef_stride = (int64_t)nrow * kMaxK;
         int r2;
         if ((r2 = bracket(step_ev))) return r2;
-        CU(launch_step(dtype, D, grid, a, c->stream, pdl && n_step > 0));
+        CU(launch_step(dtype, sf32, D, grid, a, c->stream, pdl && n_step > 0, C));
         if ((r2 = bracket(step_ev))) return r2;
         ++n_step;
         return AMC_OK;
@@ -754,13 +779,15 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         s.mean_std = dg + off_ms + row * 2;
         s.rank = drank + row;
         s.price = dg + off_price;
+        s.n_batch = C;
+        s.gamma_stride = (int64_t)nrow * kMaxK;
         int r2;
         if ((r2 = bracket(solve_ev))) return r2;
-        if (c->world == 1 || c->transport == 2) {
+        if (!exchange || c->transport == 2) {
             s.do_reduce = 1;
             s.do_solve = final_price ? 0 : 1;
             s.final_price = final_price ? 1 : 0;
-            if (c->world > 1) {
+            if (exchange) {
                 for (int q = 0; q < c->world; ++q) s.peer.mailbox[q] = (uint4*)c->peer_mailbox[q];
                 s.peer.world = c->world;
                 s.peer.rank = c->rank;
@@ -798,8 +825,9 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     }
     CU(cudaEventRecord(ev_stop, c->stream));
 
-    double price_h[2] = {0.0, 0.0};
-    CU(cudaMemcpyAsync(price_h, dg + off_price, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(price, dg + off_price, 8 * (size_t)C, cudaMemcpyDeviceToHost, c->stream));
+    if (gamma_batch_out)
+        CU(cudaMemcpyAsync(gamma_batch_out, dg + off_gamma, (size_t)C * nrow * kMaxK * 8, cudaMemcpyDeviceToHost, c->stream));
     std::vector<double> diag_h;
     std::vector<int> rank_h;
     if (steps) {
@@ -810,16 +838,22 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     }
     if (exercise_step_out && P > 0)
         CU(cudaMemcpyAsync(exercise_step_out, tau, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (cashflow0_out && P > 0)
-        CU(cudaMemcpyAsync(cashflow0_out, c->U.p, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (cashflow0_out && P > 0) {
+        if (sf32) {
+            if ((rc = ensure(c->misc, (size_t)P * 8))) return rc;
+            CU(launch_column_to_f64(AMC_F32, c->U.p, P, (double*)c->misc.p, c->stream));
+            CU(cudaMemcpyAsync(cashflow0_out, c->misc.p, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CU(cudaMemcpyAsync(cashflow0_out, c->U.p, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
     int peer_err_h = 0;
-    if (c->transport == 2) CU(cudaMemcpyAsync(&peer_err_h, c->peer_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (exchange && c->transport == 2) CU(cudaMemcpyAsync(&peer_err_h, c->peer_err, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (peer_err_h) {
         cudaMemsetAsync(c->peer_err, 0, 4, c->stream);
         return fail(AMC_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not reach the same step of the sweep");
     }
-    *price = price_h[0];
 
     if (steps) {
         if (steps->gamma) memcpy(steps->gamma, diag_h.data() + off_gamma, nrow * kMaxK * 8);
@@ -849,6 +883,51 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
         timing->other_launches = n_other;
     }
     return AMC_OK;
+}
+
+extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* spec, double* price,
+                             amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out,
+                             amc_lsm_timing* timing, int profile) {
+    if (!c || !p || !price) return fail(AMC_ERR_VALUE, "amc_lsm_price: null argument");
+    if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_lsm_price: path set belongs to another context");
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    if (exercise_step_out && !spec->want_exercise_steps)
+        return fail(AMC_ERR_VALUE, "exercise_step_out needs spec.want_exercise_steps");
+    if (spec->state_f32 && p->dtype != AMC_F32)
+        return fail(AMC_ERR_VALUE, "state_f32 needs a float32 path set (a float state under float64 paths would cap the accuracy)");
+    return lsm_sweep(c, p, spec, 1, price, steps, exercise_step_out, cashflow0_out, nullptr, timing, profile);
+}
+
+extern "C" int amc_lsm_price_batch(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, int n_contracts,
+                                   double* prices, double* gamma_out, amc_lsm_timing* timing, int profile) {
+    if (!c || !p || !prices || !specs) return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: null argument");
+    if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_lsm_price_batch: path set belongs to another context");
+    if (n_contracts < 1 || n_contracts > AMC_MAX_BATCH)
+        return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: n_contracts %d outside 1..%d", n_contracts, AMC_MAX_BATCH);
+    if (p->n_global != p->n_local)
+        return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: the path set is sharded over ranks; batches are sharded by "
+                                   "contract (every rank prices its own contracts on its own complete path sets)");
+    for (int i = 0; i < n_contracts; ++i) {
+        int rc = check_spec(&specs[i]);
+        if (rc) return rc;
+        const amc_lsm_spec &a = specs[0], &b = specs[i];
+        const bool same_barrier = (isnan(a.barrier) && isnan(b.barrier)) || a.barrier == b.barrier;
+        if (a.r != b.r || a.dt != b.dt || a.basis != b.basis || a.degree != b.degree || a.scaling != b.scaling ||
+            a.scaling_factor != b.scaling_factor || !same_barrier)
+            return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: contract %d differs from contract 0 in r/dt/basis/degree/"
+                                       "scaling/barrier; only strike, payoff side and exercise style may vary", i);
+        if (a.state_f32 != b.state_f32) return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: contract %d differs in state_f32", i);
+        if (b.state_f32 && p->dtype != AMC_F32) return fail(AMC_ERR_VALUE, "state_f32 needs a float32 path set");
+        if (b.want_exercise_steps) return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: want_exercise_steps is per contract; use amc_lsm_price");
+    }
+    if (n_contracts == 1) {
+        amc_lsm_spec one = specs[0];
+        if (gamma_out) one.want_regression = 1;
+        int rc = lsm_sweep(c, p, &one, 1, prices, nullptr, nullptr, nullptr, gamma_out, timing, profile);
+        return rc;
+    }
+    return lsm_sweep(c, p, specs, n_contracts, prices, nullptr, nullptr, nullptr, gamma_out, timing, profile);
 }
 
 extern "C" int amc_continuation(amc_ctx* c, const amc_paths* p, int t, const double* gamma, int degree, double* out) {
@@ -926,7 +1005,7 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     rc = measured_maps(c, px);
     c->world = world_saved;
     if (rc) return cleanup(rc);
-    const int grid = step_grid(c, AMC_F64, degree, n);
+    const int grid = step_grid(c, AMC_F64, 0, degree, n);
     const int64_t ldp = padded_len(n);
     if ((rc = ensure(c->U, (size_t)ldp * 8)) || (rc = ensure(c->partials, (size_t)grid * kAccStride * 8)) ||
         (rc = ensure(c->sums, kAccStride * 8)) || (rc = ensure(c->diag, (4 * kMaxK + 8) * 8)))
@@ -937,7 +1016,7 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     StepArgs a;
     memset(&a, 0, sizeof(a));
     a.x_reg = px->S;
-    a.U = (double*)c->U.p;
+    a.U = c->U.p;
     a.partials = (double*)c->partials.p;
     a.n_paths = n;
     a.t_dec = 1;
@@ -945,7 +1024,7 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     a.moments = 1;
     a.mu_reg = px->mu[0];
     a.isg_reg = 1.0 / px->sigma[0];
-    e = launch_step(AMC_F64, degree, grid, a, c->stream);
+    e = launch_step(AMC_F64, 0, degree, grid, a, c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "moment kernel: %s", cudaGetErrorString(e)));
     SolveArgs s;
     memset(&s, 0, sizeof(s));

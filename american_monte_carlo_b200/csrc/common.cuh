@@ -147,6 +147,9 @@ __device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src
 __device__ __forceinline__ void st_hint(double2* p, double2 v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
 }
+__device__ __forceinline__ void st_hint(float2* p, float2 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void st_hint(double* p, double v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
 }

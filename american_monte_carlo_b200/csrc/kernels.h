@@ -19,10 +19,19 @@ enum StepMode {
     kObserve = 2     // t < n, no early exercise: the state is only read (regression target for t-1)
 };
 
+// Contract batches (BASELINE.json config 4): several contracts priced on ONE path set in the same launches.
+// blockIdx.y selects the contract; its state vector, continuation polynomial and partial-sum rows are found through
+// the strides below, strike / payoff side / exercise style through this table (device memory).
+struct BatchContract {
+    double K;
+    int is_put;
+    int is_american;
+};
+
 struct StepArgs {
     const void* x_dec;         // column t_dec   (null when nothing is decided: kObserve)
     const void* x_reg;         // column t_dec-1 (null when moments == 0)
-    double* U;                 // per-path cashflow discounted to time 0
+    void* U;                   // per-path cashflow discounted to time 0 (double, or float with state_f32)
     int32_t* tau;              // optional exercise step per path
     const int32_t* first_hit;  // optional first knock-in step per path (barrier)
     const double* coef;        // gamma of step t_dec (device, kMaxK doubles); unused at maturity
@@ -38,6 +47,11 @@ struct StepArgs {
     double K, disc_dec;        // strike, exp(-r dt t_dec)
     double mu_dec, isg_dec;    // affine map of column t_dec:   z = (x - mu) * isg
     double mu_reg, isg_reg;    // affine map of column t_dec-1
+    // batch (null / 0 for a single contract): contract c = blockIdx.y uses U + c*u_stride, coef + c*coef_stride,
+    // partial rows [c*gridDim.x, (c+1)*gridDim.x)
+    const BatchContract* batch;
+    int64_t u_stride;
+    int64_t coef_stride;
 };
 
 // One-shot all-reduce of the moment sums over NVLink peer memory, fused into the solve kernel (multi-GPU).
@@ -70,12 +84,17 @@ struct SolveArgs {
     double* mean_std;          // [2]
     int* rank;                 // [1]
     double* price;             // [1] (final_price)
+    // batch: block c = blockIdx.x handles contract c: partials + c*n_rows rows, sums + c*kAccStride,
+    // gamma + c*gamma_stride, price + c (beta / sv / mean_std / rank are not reported for batches)
+    int n_batch;
+    int64_t gamma_stride;
     PeerArgs peer;
 };
 
-int step_grid_size(int dtype, int degree, int sm_count);
+int step_grid_size(int dtype, int state_f32, int degree, int sm_count);
 // pdl: launch as a programmatic dependent of the previous kernel in the stream (see common.cuh)
-cudaError_t launch_step(int dtype, int degree, int grid, const StepArgs& a, cudaStream_t s, bool pdl = false);
+cudaError_t launch_step(int dtype, int state_f32, int degree, int grid, const StepArgs& a, cudaStream_t s,
+                        bool pdl = false, int n_batch = 1);
 cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl = false);
 cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const double* gamma_dev, int degree, double mu,
                                 double isg, int clamp, double* out_dev, cudaStream_t s);

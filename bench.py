@@ -34,11 +34,17 @@ WORKLOADS = {
                label="BASELINE configs[0]: 100k paths x 50 steps, FP64, Power-3, injected normals"),
     "c2": dict(P=10_000_000, n=50, dtype="float64", rng="normals", basis="Power", degree=3, kw={},
                label="BASELINE configs[1]: 10M paths x 50 steps per GPU, FP64, Power-3, injected reference normals"),
-    "c3": dict(P=100_000_000, n=252, dtype="float32", rng="philox", basis="Power", degree=3, kw={}, strong=True,
+    "c3": dict(P=100_000_000, n=252, dtype="float32", state="float32", rng="philox", basis="Power", degree=3, kw={},
+               strong=True,
                label="BASELINE configs[2]: 100M paths x 252 steps TOTAL, FP32 paths / FP64 sums, Philox, sharded"),
-    "c5": dict(P=50_000_000, n=100, dtype="float32", rng="philox", basis="Laguerre", degree=8,
+    "c5": dict(P=50_000_000, n=100, dtype="float32", state="float32", rng="philox", basis="Laguerre", degree=8,
                kw=dict(scaling=True, scaling_factor=2), strong=True,
                label="BASELINE configs[4]: 50M paths x 100 steps TOTAL, degree-8 Laguerre (scaled), Philox"),
+    "c4": dict(P=1_000_000, n=50, dtype="float32", state="float32", rng="philox", basis="Power", degree=3, kw={},
+               strong=True, grid=True,
+               label="BASELINE configs[3]: 1024 contracts (16 strikes x 8 vols x 8 maturities), 1M paths x 50 steps "
+                     "each, FP32 paths / FP64 sums, Philox; strikes of a (vol, maturity) cell batched on one path set, "
+                     "cells sharded over GPUs"),
 }
 GOLDEN_C2_PRICE = 4.475181386178888      # tests/golden/golden.json, reference run, seed 42
 
@@ -164,6 +170,111 @@ def run_reference(args, wl, rank, emit):
     }))
 
 
+def run_contract_grid(args, wl, ctx, world, rank, local_rank, dev, stream, emit):
+    """Workload c4: the whole 1024-contract grid is one step (64 path sets, 16 strikes batched on each)."""
+    import torch
+    import torch.distributed as dist
+    from american_monte_carlo_b200 import sweeps
+
+    strikes, vols, mats = sweeps.default_contract_grid()
+    n, P = wl["n"], wl["P"]
+    n_contracts = len(strikes) * len(vols) * len(mats)
+    cells = len(vols) * len(mats)
+    my_cells = len([i for i in range(cells) if i % world == rank])
+    bS = 4 if wl["dtype"] == "float32" else 8
+    bU = 4 if wl["state"] == "float32" else 8
+
+    def one_step(profile=False):
+        tm = []
+        prices = sweeps.contract_grid(LS_PUT["S0"], LS_PUT["r"], strikes, vols, mats, n, P, "Put", "American", None,
+                                      wl["basis"], wl["degree"], seed=42, dtype=wl["dtype"], ctx=ctx, combine=True,
+                                      on_cell=lambda iv, im, t: tm.append(t), profile=profile, state_dtype=wl["state"])
+        return prices, tm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps, profile=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = [one_step(profile) for _ in range(steps)]
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+        sampler.mark("begin")
+    ms, out = timed(args.steps)
+    _, prof = timed(1, profile=True)
+    if rank == 0:
+        sampler.mark("end")
+    clocks = sampler.stop() if rank == 0 else None
+
+    C = len(strikes)
+    unit_steps = float(n_contracts) * P * n
+    value = unit_steps * args.steps / (ms * 1e-3)
+    tms = prof[0][1]
+    step_ms = sum(t["step_kernel_ms"] for t in tms)
+    sweep_ms = sum(t["total_ms"] for t in out[-1][1])
+    launches = sum(t["step_launches"] for t in tms)
+    # batched launch: the two columns are read once for the whole batch, the state once per contract
+    alg_bytes = my_cells * P * ((2 * bS + bU * C) + (n - 1) * (2 * bS + 2 * bU * C) + (bS + 2 * bU * C))
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    prices = out[-1][0]
+    line = {
+        "metric": "LSM path-steps/sec (path simulation + backward induction)", "value": value,
+        "unit": "path-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 sums over f32 paths (%s state)" % wl["state"],
+        "data": "synthetic: device Philox4x32-10 + Box-Muller, seed 42 + cell index",
+        "config": {"workload": "c4", "description": wl["label"], "contracts": n_contracts,
+                   "strikes": [float(strikes[0]), float(strikes[-1]), len(strikes)],
+                   "vols": [float(vols[0]), float(vols[-1]), len(vols)],
+                   "maturities": [float(mats[0]), float(mats[-1]), len(mats)],
+                   "paths_per_contract": P, "time_steps": n, "basis": wl["basis"], "degree": wl["degree"],
+                   "path_dtype": wl["dtype"], "state_dtype": wl["state"], "rng": "philox",
+                   "unit_definition": "contract x path x step",
+                   "l2": "per step and cell the batch streams 16 state vectors (128 MB) -- larger than L2; the two "
+                         "4 MB path columns are L2-resident by design"},
+        "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": n_contracts * 8, "ms_per_step": ms / args.steps,
+                "api": "sweeps.contract_grid = amc_paths_generate + amc_lsm_price_batch per (vol, maturity) cell; no host "
+                       "input exists for this workload (device Philox), prices are read back per cell"},
+        "gpu_launches": int(args.steps * sum(1 + t["step_launches"] + t["solve_launches"] for t in tms)),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "lsm_step_tma_kernel, grid.y = 16 contracts (batched decision + moments)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
+                     "launches_per_sweep": launches, "avg_launch_ms": step_ms / max(launches, 1),
+                     "how": "CUDA events around every launch on the launching stream, separate profiled pass"},
+        "breakdown_ms": {"sweeps_total": sweep_ms, "step_kernels": step_ms,
+                         "pathgen_and_host": ms / args.steps - sweep_ms},
+        "price_grid_corners": [float(prices[0, 0, 0]), float(prices[-1, 0, 0]), float(prices[0, -1, -1]),
+                               float(prices[-1, -1, -1])],
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_oracle_rate(wl, 1_000_000)
+        cb.pop("seconds", None)
+        cb["sample"] = "ONE contract of the grid (K=40, sigma=0.2, T=1): " + cb["sample"]
+        line["cpu_baseline"] = cb
+    if rank == 0:
+        emit(json.dumps(line))
+
+
 def claim_stdout():
     """Route everything libraries print to stdout (e.g. NCCL's version banner) to stderr; return a writer for the
     one JSON line the contract allows on stdout."""
@@ -185,11 +296,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--paths", type=int, default=None, help="override paths (per GPU; total for c3/c5)")
+    ap.add_argument("--state", default=None, choices=["float64", "float32"],
+                    help="storage of the per-path state (default: float64 for FP64 workloads, float32 for FP32-path ones)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.paths:
         wl["P"] = args.paths
+    wl["state"] = args.state or wl.get("state", "float64")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,6 +341,12 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.init_comm(world, rank, ids[0])
 
+    if wl.get("grid"):
+        run_contract_grid(args, wl, ctx, world, rank, local_rank, dev, stream, emit)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     n = wl["n"]
     strong = wl.get("strong", False)
     if strong:
@@ -238,6 +358,7 @@ def main():
     P_local = hi - lo
     did = N.F64 if wl["dtype"] == "float64" else N.F32
     bS = 8 if did == N.F64 else 4
+    bU = 4 if wl["state"] == "float32" else 8
     dt = LS_PUT["T"] / n
     price_args = (LS_PUT["K"], LS_PUT["r"], dt, "Put", None, "American", wl["basis"], wl["degree"])
 
@@ -284,7 +405,7 @@ def main():
 
     def one_step(from_host, profile=False):
         dp = make_paths(from_host)
-        res = amc.lsm_price(dp, *price_args, **wl["kw"], profile=profile, ctx=ctx)
+        res = amc.lsm_price(dp, *price_args, **wl["kw"], state_dtype=wl["state"], profile=profile, ctx=ctx)
         dp.free()
         return res
 
@@ -334,10 +455,10 @@ def main():
     tm = res_prof[-1].timing
     step_launches = tm["step_launches"]
     # algorithmic bytes of the fused decide+moments launches of one sweep (DESIGN.md "Kernels"):
-    #   maturity launch: read S_n, S_{n-1}, write state                      2 b_S + 8
-    #   n-1 middle launches: read S_t, S_{t-1}, read+write state             2 b_S + 16
-    #   last launch (t = 0): read S_0, read+write state                      b_S + 16
-    alg_bytes = P_local * ((2 * bS + 8) + (n - 1) * (2 * bS + 16) + (bS + 16))
+    #   maturity launch: read S_n, S_{n-1}, write state                      2 b_S + b_U
+    #   n-1 middle launches: read S_t, S_{t-1}, read+write state             2 b_S + 2 b_U
+    #   last launch (t = 0): read S_0, read+write state                      b_S + 2 b_U      (b_U = 8 or 4)
+    alg_bytes = P_local * ((2 * bS + bU) + (n - 1) * (2 * bS + 2 * bU) + (bS + 2 * bU))
     step_ms = statistics.mean(r.timing["step_kernel_ms"] for r in res_prof)
     solve_ms = statistics.mean(r.timing["solve_kernel_ms"] for r in res_prof)
     sweep_ms = statistics.mean(r.timing["total_ms"] for r in res_dev)
@@ -358,10 +479,11 @@ def main():
         "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None,
-        "dtype": "f64" if did == N.F64 else "f64 sums over f32 paths", "data": data,
+        "dtype": "f64" if did == N.F64 else "f64 sums over f32 paths (%s state)" % wl["state"], "data": data,
         "config": {"workload": args.workload, "description": wl["label"], "contract": "American put " + json.dumps(LS_PUT),
                    "paths_per_gpu": P_local, "paths_total": P_global, "time_steps": n, "basis": wl["basis"],
-                   "degree": wl["degree"], "path_dtype": wl["dtype"], "rng": wl["rng"], "allreduce": ctx.transport,
+                   "degree": wl["degree"], "path_dtype": wl["dtype"], "state_dtype": wl["state"], "rng": wl["rng"],
+                   "allreduce": ctx.transport,
                    "l2": "inputs larger than L2 (path matrix %.1f GB per GPU re-streamed every step)" % (P_local * (n + 1) * bS / 1e9)},
         "e2e": {"value": e2e_value, "unit": "path-steps/s",
                 "h2d_bytes_per_step": (P_local * n * 8 if wl["rng"] == "normals" else 0) * world,

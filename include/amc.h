@@ -118,6 +118,10 @@ typedef struct amc_lsm_spec {
     int want_exercise_steps; /* keep a per-path exercise-step array on the device (tests / diagnostics) */
     int want_svd;            /* always run the k x k SVD and report singular values (otherwise it is skipped on
                                 steps whose full rank is certified cheaply; prices do not depend on this) */
+    int state_f32;           /* keep the per-path state (cashflow discounted to time 0) in float instead of double:
+                                FP32-path mode only (AMC_F32 path sets); all sums, the solve and the exercise test stay
+                                in double.  Halves the state traffic (2 b_S + 8 instead of 2 b_S + 16 bytes per
+                                path-step); price effect ~1e-8 relative, inside the 1e-5 FP32 tolerance */
 } amc_lsm_spec;
 
 /* per-step diagnostics, all indexed by t = 0..n_time_steps (entry n is unused: no regression at maturity) */
@@ -146,6 +150,18 @@ typedef struct amc_lsm_timing {
 int amc_lsm_price(amc_ctx* ctx, const amc_paths* paths, const amc_lsm_spec* spec, double* price,
                   amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out,
                   amc_lsm_timing* timing, int profile);
+
+/* Price `n_contracts` contracts on ONE device-resident path set in the same launches (BASELINE.json config 4: the
+ * strike axis of a strike x vol x maturity grid shares its paths; the reference re-simulates and re-prices per
+ * contract in a Python loop, american_monte_carlo_additional_plots.py:100-107).  The contracts may differ in K,
+ * is_put and is_american; r, dt, barrier, basis, degree, scaling and scaling_factor must equal those of specs[0].
+ * Each contract's result is the one amc_lsm_price gives for it alone (same arithmetic; the partial sums are grouped
+ * differently, so agreement is to rounding, not bitwise).  prices: [n_contracts]; gamma_out (optional):
+ * [n_contracts][n_time_steps+1][AMC_MAX_K].  Multi-GPU use shards the CONTRACTS (and their path sets) over ranks:
+ * the path set passed here must be complete (n_paths_local == n_paths_global); no collective is involved. */
+#define AMC_MAX_BATCH 256
+int amc_lsm_price_batch(amc_ctx* ctx, const amc_paths* paths, const amc_lsm_spec* specs, int n_contracts,
+                        double* prices, double* gamma_out, amc_lsm_timing* timing, int profile);
 
 /* Continuation value max(fit, 0) of every local path at step t from a stored gamma (lazy replacement for the
  * per-step copies of amc.py:164).  out: host [n_paths_local]. */

@@ -126,6 +126,34 @@ def test_fp32_path_storage_within_1e5(amc, golden):
     assert (res.exercise_steps != o.exercise_times).mean() < 1e-3
 
 
+@pytest.mark.parametrize("name", ["c1_power3", "ut_Put_American_80", "small_legendre8_scaled", "c1_call_power3"])
+def test_fp32_state_within_1e5(amc, golden, name):
+    """state_f32: the per-path state (cashflow discounted to time 0) is stored as float; sums, solve and the exercise
+    test stay in double.  Against the FP64 oracle the FP32 tolerance (1e-5) applies; against the same sweep with a
+    double state the difference is the state's rounding only."""
+    c = golden[name]
+    Z, paths, o = oracle_case(c)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"], dtype="float32")
+    r64 = amc.lsm_price(dp, *price_args(c), **c["kwargs"], want_exercise_steps=True, want_cashflows=True)
+    r32 = amc.lsm_price(dp, *price_args(c), **c["kwargs"], want_exercise_steps=True, want_cashflows=True,
+                        state_dtype="float32")
+    assert rel(r32.price, c["price"]) <= 1e-5
+    assert rel(r32.price, r64.price) <= 2e-7
+    assert (r32.exercise_steps != r64.exercise_steps).mean() < 1e-4
+    same = r32.exercise_steps == r64.exercise_steps
+    np.testing.assert_allclose(r32.cashflow0[same], r64.cashflow0[same], rtol=1e-6, atol=0)
+    # batched sweep with a float state
+    b32 = amc.lsm_price_batch(dp, [(c["K"], c["option_type"], c["exercise_type"])] * 3, c["r"],
+                              c["T"] / c["n_time_steps"], c["barrier_level"], c["basis_type"], c["degree"],
+                              state_dtype="float32", **c["kwargs"])
+    assert np.all(np.abs(b32 - r32.price) <= 1e-9 * max(abs(r32.price), 1e-3))
+    dp.free()
+    d64 = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    with pytest.raises(ValueError):
+        amc.lsm_price(d64, *price_args(c), **c["kwargs"], state_dtype="float32")
+    d64.free()
+
+
 def test_philox_paths_statistics_and_price_within_mc_error(amc, golden):
     c = golden["c1_power3"]
     P, n = 400_000, c["n_time_steps"]
@@ -261,3 +289,66 @@ def test_config2_10M_paths_fp64_injected_normals(amc, golden):
     assert moved == 0, f"exercise-step histogram differs by {moved}"
     assert int(np.count_nonzero(res.cashflow0)) == c["n_nonzero_cashflows"]
     assert rel(res.price, c["price"]) <= 1e-10
+
+
+# ------------------------------------------------------------------------------------------------ contract batches
+def _batch_contracts():
+    # strike axis of a sweep, both payoff sides, both exercise styles -- all on one path set
+    return [(40.0, "Put", "American"), (36.0, "Put", "American"), (44.0, "Put", "American"), (38.0, "Call", "American"),
+            (40.0, "Put", "European"), (34.0, "Call", "European"), (32.0, "Put", "American")]
+
+
+@pytest.mark.parametrize("basis,degree,kwargs", [("Power", 3, {}), ("Chebyshev", 4, {}),
+                                                 ("Legendre", 8, dict(scaling=True, scaling_factor=2))])
+def test_batch_equals_oracle_per_contract(amc, basis, degree, kwargs):
+    """amc_lsm_price_batch: every contract of a batch must reproduce the oracle's price for that contract alone
+    (identical injected normals, 1e-10) and the price amc_lsm_price gives for it (rounding only)."""
+    S0, r, sigma, T, n, P = 36.0, 0.06, 0.2, 1.0, 40, 60_000
+    np.random.seed(123)
+    Z = orc.draw_normals(P, n)
+    paths = orc.paths_from_normals(Z, S0, r, sigma, T)
+    dp = amc.paths_from_normals(Z, S0, r, sigma, T)
+    contracts = _batch_contracts()
+    got, gamma = amc.lsm_price_batch(dp, contracts, r, T / n, None, basis, degree, want_gamma=True, **kwargs)
+    assert got.shape == (len(contracts),) and gamma.shape == (len(contracts), n + 1, 11)
+    for i, (K, opt, ex) in enumerate(contracts):
+        want = orc.lsm_backward(paths, K, r, T / n, opt, None, ex, basis, degree, keep_continuation=False, **kwargs)
+        solo = amc.lsm_price(dp, K, r, T / n, opt, None, ex, basis, degree, **kwargs)
+        assert rel(got[i], want.price) <= 1e-10 or abs(got[i] - want.price) <= 1e-14, (i, got[i], want.price)
+        assert rel(got[i], solo.price) <= 1e-12 or abs(got[i] - solo.price) <= 1e-14
+        if ex == "American":
+            np.testing.assert_allclose(gamma[i, 1:n], solo.gamma[1:n], rtol=1e-7, atol=1e-9)
+    dp.free()
+
+
+def test_batch_with_barrier_and_f32_paths(amc):
+    S0, r, sigma, T, n, P = 100.0, 0.01, 0.2, 1.0, 30, 50_000
+    np.random.seed(7)
+    Z = orc.draw_normals(P, n)
+    paths = orc.paths_from_normals(Z, S0, r, sigma, T)
+    dp = amc.paths_from_normals(Z, S0, r, sigma, T)
+    contracts = [(100.0, "Put", "American"), (95.0, "Put", "American"), (105.0, "Put", "European")]
+    got = amc.lsm_price_batch(dp, contracts, r, T / n, 80.0, "Power", 3, scaling=True)
+    for i, (K, opt, ex) in enumerate(contracts):
+        want = orc.lsm_backward(paths, K, r, T / n, opt, 80.0, ex, "Power", 3, keep_continuation=False, scaling=True)
+        assert rel(got[i], want.price) <= 1e-10
+    dp.free()
+    d32 = amc.paths_from_normals(Z, S0, r, sigma, T, dtype="float32")
+    got32 = amc.lsm_price_batch(d32, contracts, r, T / n, None, "Power", 3, scaling=True)
+    for i, (K, opt, ex) in enumerate(contracts):
+        want = orc.lsm_backward(paths, K, r, T / n, opt, None, ex, "Power", 3, keep_continuation=False, scaling=True)
+        assert rel(got32[i], want.price) <= 1e-5                       # FP32 path storage tolerance (north_star)
+    d32.free()
+
+
+def test_batch_argument_errors(amc):
+    dp = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 5, 1000, rng="philox", seed=1)
+    with pytest.raises(ValueError):
+        amc.lsm_price_batch(dp, [(40.0, "Put", "American")] * 300, 0.06, 0.2, None, "Power", 3)     # > AMC_MAX_BATCH
+    with pytest.raises(ValueError):
+        amc.lsm_price_batch(dp, [(40.0, "Put", "American")], 0.06, 0.2, None, "Hermite", 3)
+    assert amc.lsm_price_batch(dp, [], 0.06, 0.2).shape == (0,)
+    one = amc.lsm_price_batch(dp, [(40.0, "Put", "American")], 0.06, 0.2, None, "Power", 3)
+    solo = amc.lsm_price(dp, 40.0, 0.06, 0.2, "Put", None, "American", "Power", 3)
+    assert one[0] == solo.price
+    dp.free()
