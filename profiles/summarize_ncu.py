@@ -46,6 +46,24 @@ def kernel(path):
     for i, h in enumerate(hdr):
         if h in METRICS:
             print(f"{h:70s} {units[i]:14s} {[r[i] for r in data]}")
+    # top warp-stall reasons of the first captured launch (share of warp-active cycles)
+    stalls = []
+    for i, h in enumerate(hdr):
+        if "issue_stalled" in h and h.endswith("per_warp_active.pct") and data:
+            try:
+                stalls.append((float(data[0][i].replace(",", "")), h))
+            except ValueError:
+                pass
+    for v, h in sorted(stalls, reverse=True)[:7]:
+        print(f"{h:90s} {v:8.2f}")
+    for i, h in enumerate(hdr):
+        if h.startswith("sm__inst_executed_pipe_") and h.endswith(".sum") and data:
+            try:
+                v = float(data[0][i].replace(",", ""))
+            except ValueError:
+                continue
+            if v > 0:
+                print(f"{h:70s} {units[i]:14s} {data[0][i]}")
 
 
 if __name__ == "__main__":
