@@ -697,9 +697,8 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     if (barrier && P > 0)
         CU(launch_first_hit(dtype, p->S, p->ld, n + 1, P, spec->barrier, fh, c->stream));
 
-    // L2 management knobs (on by default; AMC_L2_REVERSE=0 / AMC_L2_HINTS=0 for A/B measurements)
+    // L2 management knob (on by default; AMC_L2_REVERSE=0 for A/B measurements)
     static const int opt_reverse = getenv("AMC_L2_REVERSE") ? atoi(getenv("AMC_L2_REVERSE")) : 1;
-    static const int opt_hints = getenv("AMC_L2_HINTS") ? atoi(getenv("AMC_L2_HINTS")) : 1;
     // programmatic dependent launch along the K3 -> K4 -> K3 chain (single GPU, not while profiling: the
     // per-launch events and the NCCL kernels are ordinary stream dependencies)
     static const int opt_pdl = getenv("AMC_PDL") ? atoi(getenv("AMC_PDL")) : 1;
@@ -744,7 +743,6 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         a.moments = moments ? 1 : 0;
         a.is_put = spec->is_put;
         a.reverse = opt_reverse ? (t & 1) : 0;
-        a.l2_hints = opt_hints;
         a.K = spec->K;
         a.disc_dec = exp(-rdt * (double)t);
         a.mu_dec = p->mu[t];

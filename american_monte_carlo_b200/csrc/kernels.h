@@ -43,7 +43,6 @@ struct StepArgs {
     int is_put;
     int reverse;               // walk the tiles from the high end: consecutive launches alternate direction so the
                                // tail of what launch t touched last (S_{t-1}, U) is still in L2 when launch t-1 starts
-    int l2_hints;              // use evict_first / evict_last policies on the tile copies and state stores
     double K, disc_dec;        // strike, exp(-r dt t_dec)
     double mu_dec, isg_dec;    // affine map of column t_dec:   z = (x - mu) * isg
     double mu_reg, isg_reg;    // affine map of column t_dec-1

@@ -136,14 +136,11 @@ constexpr int kTile = 1024;       // paths per tile
 constexpr int kStages = 4;
 
 // updated state of two adjacent paths: one 16-byte (f64 state) or 8-byte (f32 state) store
-__device__ __forceinline__ void store_state2(double* dst, double2 u, int hints, uint64_t policy) {
-    if (hints) st_hint(reinterpret_cast<double2*>(dst), u, policy);
-    else *reinterpret_cast<double2*>(dst) = u;
+__device__ __forceinline__ void store_state2(double* dst, double2 u, uint64_t policy) {
+    st_hint(reinterpret_cast<double2*>(dst), u, policy);
 }
-__device__ __forceinline__ void store_state2(float* dst, double2 u, int hints, uint64_t policy) {
-    const float2 v = make_float2((float)u.x, (float)u.y);
-    if (hints) st_hint(reinterpret_cast<float2*>(dst), v, policy);
-    else *reinterpret_cast<float2*>(dst) = v;
+__device__ __forceinline__ void store_state2(float* dst, double2 u, uint64_t policy) {
+    st_hint(reinterpret_cast<float2*>(dst), make_float2((float)u.x, (float)u.y), policy);
 }
 
 template <typename XT, typename UT>
@@ -171,15 +168,10 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
     using U2 = typename Vec2<UT>::type;
 
     pdl_launch_dependents();     // let the solve kernel of this step become resident right away
-    pdl_wait();                  // ... and do not touch memory before the previous solve has finished
 
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-    double gam[D + 1];
-#pragma unroll
-    for (int i = 0; i <= D; ++i) gam[i] = (a.mode == kDecide) ? a.coef[i] : 0.0;
-
     const XT* xdec = static_cast<const XT*>(a.x_dec);
     const XT* xreg = static_cast<const XT*>(a.x_reg);
     const bool need_dec = (a.mode != kObserve);
@@ -188,6 +180,10 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
 
     const int64_t n_tiles = (a.n_paths + kTile - 1) / kTile;
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles blockIdx.x + i*grid
+    // this block's tiles as a running path offset: first + i * stride (stride < 0 when the launch walks the column
+    // from the high end, see StepArgs::reverse)
+    const int64_t p_first = (a.reverse ? (n_tiles - 1 - (int64_t)blockIdx.x) : (int64_t)blockIdx.x) * kTile;
+    const int64_t p_stride = (a.reverse ? -(int64_t)gridDim.x : (int64_t)gridDim.x) * kTile;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -196,37 +192,39 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
     }
     __syncthreads();
 
+    // L2 is managed explicitly: S_t is dead after this launch (evict_first); S_{t-1} and the state are re-read by the
+    // next launch (evict_last).  A/B of the policies: profiles/r1c_l2_ab.txt.
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-    auto tile_of = [&](int i) -> int64_t {
-        const int64_t fwd = blockIdx.x + (int64_t)i * gridDim.x;
-        return a.reverse ? (n_tiles - 1 - fwd) : fwd;
-    };
-    auto issue = [&](int i) {           // thread 0 only: start the copies of this block's i-th tile
-        const int64_t tile = tile_of(i);
-        const int64_t p0 = tile * kTile;
+    // thread 0 only: start the copies of the tile at path offset p0 into stage s.  parts bit 0: arm the barrier with
+    // the tile's total byte count and copy the two path columns; bit 1: copy the state.  (Split because the columns
+    // are immutable and may be fetched before the programmatic-dependency wait, the state may not.)
+    auto issue = [&](int64_t p0, int s, int parts) {
         int64_t valid = a.n_paths - p0;
         if (valid > kTile) valid = kTile;
         const uint32_t elems = (uint32_t)((valid + 31) / 32 * 32);     // columns are padded to 32 elements
-        const int s = i % kStages;
         unsigned char* st = ring + (size_t)s * StageBytes<XT, UT>::value;
         const uint32_t bx = elems * (uint32_t)sizeof(XT), bu = elems * (uint32_t)sizeof(UT);
-        const uint32_t total = (need_dec ? bx : 0u) + (a.moments ? bx : 0u) + (need_u_in ? bu : 0u);
-        mbar_expect_tx(&full[s], total);
-        if (a.l2_hints) {
-            // S_t is dead after this launch; S_{t-1} and U are re-read by the next launch
+        if (parts & 1) {
+            mbar_expect_tx(&full[s], (need_dec ? bx : 0u) + (a.moments ? bx : 0u) + (need_u_in ? bu : 0u));
             if (need_dec) tma_load_1d_hint(st, xdec + p0, bx, &full[s], pol_stream);
             if (a.moments) tma_load_1d_hint(st + kTile * sizeof(XT), xreg + p0, bx, &full[s], pol_keep);
-            if (need_u_in) tma_load_1d_hint(st + 2 * kTile * sizeof(XT), Ug + p0, bu, &full[s], pol_keep);
-        } else {
-            if (need_dec) tma_load_1d(st, xdec + p0, bx, &full[s]);
-            if (a.moments) tma_load_1d(st + kTile * sizeof(XT), xreg + p0, bx, &full[s]);
-            if (need_u_in) tma_load_1d(st + 2 * kTile * sizeof(XT), Ug + p0, bu, &full[s]);
         }
+        if ((parts & 2) && need_u_in) tma_load_1d_hint(st + 2 * kTile * sizeof(XT), Ug + p0, bu, &full[s], pol_keep);
     };
 
+    // prologue: the path columns of the first tiles are on their way while the previous kernel of the chain (the
+    // solve of this step) is still finishing; the state and the polynomial are touched only after the wait
+    int64_t p_issue = p_first;                           // thread 0: offset of the next tile to be issued
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages - 1 && i < my_tiles; ++i) issue(i);
+        for (int i = 0; i < kStages - 1 && i < my_tiles; ++i) issue(p_first + i * p_stride, i, 1);
     }
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages - 1 && i < my_tiles; ++i) { issue(p_issue, i, 2); p_issue += p_stride; }
+    }
+    double gam[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) gam[i] = (a.mode == kDecide) ? a.coef[i] : 0.0;
 
     using V2 = typename Vec2<XT>::type;
     const bool fast_ok = (a.mode == kDecide) && a.moments && !a.first_hit && !a.tau;
@@ -236,63 +234,70 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
     fc.da = a.isg_dec; fc.db = -a.mu_dec * a.isg_dec;
     fc.ra = a.isg_reg; fc.rb = -a.mu_reg * a.isg_reg;
     fc.disc = a.disc_dec;
-    for (int i = 0; i < my_tiles; ++i) {
-        const int s = i % kStages;
-        if (threadIdx.x == 0 && i + kStages - 1 < my_tiles) issue(i + kStages - 1);
-        mbar_wait(&full[s], (uint32_t)((i / kStages) & 1));
+    constexpr int NK = kTile / 2 / kStepThreads;
+    int64_t p0 = p_first;
+    int s = 0, s_issue = (kStages - 1) % kStages;
+    uint32_t phase = 0;
+    for (int i = 0; i < my_tiles; ++i, p0 += p_stride) {
+        if (threadIdx.x == 0 && i + kStages - 1 < my_tiles) {
+            issue(p_issue, s_issue, 3);
+            p_issue += p_stride;
+        }
+        s_issue = (s_issue + 1 == kStages) ? 0 : s_issue + 1;
+        mbar_wait(&full[s], phase);
 
-        const int64_t tile = tile_of(i);
-        const int64_t p0 = tile * kTile;
-        int64_t valid64 = a.n_paths - p0;
-        const int valid = (int)(valid64 > kTile ? kTile : valid64);
         const unsigned char* st = ring + (size_t)s * StageBytes<XT, UT>::value;
-        const V2* sxd = reinterpret_cast<const V2*>(st);
-        const V2* sxr = reinterpret_cast<const V2*>(st + kTile * sizeof(XT));
-        const U2* su = reinterpret_cast<const U2*>(st + 2 * kTile * sizeof(XT));
+        const V2* sxd = reinterpret_cast<const V2*>(st) + threadIdx.x;
+        const V2* sxr = reinterpret_cast<const V2*>(st + kTile * sizeof(XT)) + threadIdx.x;
+        const U2* su = reinterpret_cast<const U2*>(st + 2 * kTile * sizeof(XT)) + threadIdx.x;
 
-        if (fast_ok && valid == kTile) {
+        if (fast_ok && p0 + kTile <= a.n_paths) {
+            UT* const up = Ug + p0 + 2 * threadIdx.x;
 #pragma unroll
-            for (int k = 0; k < kTile / 2 / kStepThreads; ++k) {
-                const int j = threadIdx.x + k * kStepThreads;
-                const V2 vd = sxd[j], vr = sxr[j];
-                const U2 uv = su[j];
+            for (int k = 0; k < NK; ++k) {
+                const V2 vd = sxd[k * kStepThreads], vr = sxr[k * kStepThreads];
+                const U2 uv = su[k * kStepThreads];
                 double2 u = make_double2((double)uv.x, (double)uv.y);
                 bool changed = fast_path_step<D>(fc, gam, (double)vd.x, (double)vr.x, u.x, acc);
                 changed |= fast_path_step<D>(fc, gam, (double)vd.y, (double)vr.y, u.y, acc);
-                if (changed) store_state2(Ug + p0 + 2 * j, u, a.l2_hints, pol_keep);
+                // the state is written only where a path exercised (one vector store per pair): below maturity most
+                // pairs are untouched, which removes most of the write traffic
+                if (changed) store_state2(up + 2 * k * kStepThreads, u, pol_keep);
             }
-        } else
+        } else {
+            int64_t valid64 = a.n_paths - p0;
+            const int valid = (int)(valid64 > kTile ? kTile : valid64);
 #pragma unroll
-        for (int k = 0; k < kTile / 2 / kStepThreads; ++k) {
-            const int j = threadIdx.x + k * kStepThreads;        // pair index inside the tile
-            const int e0 = 2 * j;
-            if (e0 < valid) {
-                const bool two = (e0 + 1 < valid);
-                double xd0 = 0, xd1 = 0, xr0 = 0, xr1 = 0;
-                double2 u = make_double2(0.0, 0.0);
-                int2 f = make_int2(0, 0), t = make_int2(0, 0);
-                if (need_dec) { const V2 v = sxd[j]; xd0 = (double)v.x; xd1 = (double)v.y; }
-                if (a.moments) { const V2 v = sxr[j]; xr0 = (double)v.x; xr1 = (double)v.y; }
-                if (need_u_in) { const U2 uv = su[j]; u = make_double2((double)uv.x, (double)uv.y); }
-                const int64_t p = p0 + e0;
-                if (a.first_hit) { f.x = __ldg(a.first_hit + p); if (two) f.y = __ldg(a.first_hit + p + 1); }
-                if (a.tau && need_u_in) { t.x = a.tau[p]; if (two) t.y = a.tau[p + 1]; }
-                bool changed = path_step<D>(a, gam, xd0, xr0, u.x, t.x, f.x, acc);
-                if (two) changed |= path_step<D>(a, gam, xd1, xr1, u.y, t.y, f.y, acc);
-                // the state is written only where a path exercised (16-byte granularity): below maturity
-                // most pairs are untouched, which removes most of the write traffic
-                if (write_u && changed) {
-                    if (two) {
-                        store_state2(Ug + p, u, a.l2_hints, pol_keep);
-                        if (a.tau) *reinterpret_cast<int2*>(a.tau + p) = t;
-                    } else {
-                        Ug[p] = (UT)u.x;
-                        if (a.tau) a.tau[p] = t.x;
+            for (int k = 0; k < NK; ++k) {
+                const int j = threadIdx.x + k * kStepThreads;        // pair index inside the tile
+                const int e0 = 2 * j;
+                if (e0 < valid) {
+                    const bool two = (e0 + 1 < valid);
+                    double xd0 = 0, xd1 = 0, xr0 = 0, xr1 = 0;
+                    double2 u = make_double2(0.0, 0.0);
+                    int2 f = make_int2(0, 0), t = make_int2(0, 0);
+                    if (need_dec) { const V2 v = sxd[k * kStepThreads]; xd0 = (double)v.x; xd1 = (double)v.y; }
+                    if (a.moments) { const V2 v = sxr[k * kStepThreads]; xr0 = (double)v.x; xr1 = (double)v.y; }
+                    if (need_u_in) { const U2 uv = su[k * kStepThreads]; u = make_double2((double)uv.x, (double)uv.y); }
+                    const int64_t p = p0 + e0;
+                    if (a.first_hit) { f.x = __ldg(a.first_hit + p); if (two) f.y = __ldg(a.first_hit + p + 1); }
+                    if (a.tau && need_u_in) { t.x = a.tau[p]; if (two) t.y = a.tau[p + 1]; }
+                    bool changed = path_step<D>(a, gam, xd0, xr0, u.x, t.x, f.x, acc);
+                    if (two) changed |= path_step<D>(a, gam, xd1, xr1, u.y, t.y, f.y, acc);
+                    if (write_u && changed) {
+                        if (two) {
+                            store_state2(Ug + p, u, pol_keep);
+                            if (a.tau) *reinterpret_cast<int2*>(a.tau + p) = t;
+                        } else {
+                            Ug[p] = (UT)u.x;
+                            if (a.tau) a.tau[p] = t.x;
+                        }
                     }
                 }
             }
         }
         __syncthreads();                 // every warp is done with stage s before it is refilled
+        if (++s == kStages) { s = 0; phase ^= 1u; }
     }
     block_reduce_store<NACC, kStepThreads, kAccStride>(acc, red, a.partials + (int64_t)blockIdx.x * kAccStride);
 }
