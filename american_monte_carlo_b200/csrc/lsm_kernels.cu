@@ -42,25 +42,38 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
     pdl_launch_dependents();
     pdl_wait();
     if (a.do_reduce) {
-        // rows are 32 doubles: lane = accumulator, warp = row group; loads are coalesced and issued in batches
-        // of 8 so the latency of the (L2-resident) partials is paid a handful of times, not once per row.
-        // Summation order is fixed (row group, then rows ascending, then groups ascending): deterministic.
+        // A partial row is 32 doubles of which the first nacc are used: LPR lanes read one row, so a warp covers
+        // 32 / LPR rows per load.  Every thread issues 16 independent (predicated) loads per round: the latency of the
+        // L2-resident partials is paid ceil(rows / (16 * slots)) times -- 3 rounds for a full grid -- not once per row.
+        // Summation order is fixed (slot, then rows ascending, then slots ascending): deterministic.
+        constexpr int LPR = nacc <= 8 ? 8 : (nacc <= 16 ? 16 : 32);
+        constexpr int RPW = 32 / LPR;
+        constexpr int NSLOT = (kSolveThreads / 32) * RPW;
+        const int col = lane % LPR;
+        const int slot = grp * RPW + lane / LPR;
+        // contract batches: the power sums (columns < 2d) are taken from contract 0's rows (see lsm_step.cuh)
+        const double* src = (col < 2 * d) ? a_in.partials : a.partials;
         double v = 0.0;
-        int row = grp;
-        for (; row + 7 * (kSolveThreads / 32) < a.n_rows; row += 8 * (kSolveThreads / 32)) {
-            double t[8];
+        for (int row0 = slot; row0 < a.n_rows; row0 += 16 * NSLOT) {
+            double t[16];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = a.partials[(int64_t)(row + q * (kSolveThreads / 32)) * kAccStride + lane];
+            for (int q = 0; q < 16; ++q) {
+                const int r = row0 + q * NSLOT;
+                t[q] = (r < a.n_rows) ? src[(int64_t)r * kAccStride + col] : 0.0;
+            }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v += t[q];
+            for (int q = 0; q < 16; ++q) v += t[q];
         }
-        for (; row < a.n_rows; row += kSolveThreads / 32) v += a.partials[(int64_t)row * kAccStride + lane];
-        part[grp][lane] = v;
+        double* flat = &part[0][0];                       // [NSLOT][LPR] = 256 doubles
+        flat[slot * LPR + col] = v;
+        __syncthreads();
+        double tot = 0.0;
+        if (threadIdx.x < nacc) {
+#pragma unroll
+            for (int q = 0; q < NSLOT; ++q) tot += flat[q * LPR + threadIdx.x];
+        }
         __syncthreads();
         if (threadIdx.x < nacc) {
-            double tot = 0.0;
-#pragma unroll
-            for (int q = 0; q < kSolveThreads / 32; ++q) tot += part[q][threadIdx.x];
             a.sums[threadIdx.x] = tot;
             part[0][threadIdx.x] = tot;
         }

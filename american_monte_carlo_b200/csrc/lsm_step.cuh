@@ -96,7 +96,7 @@ struct FastConsts {
 // acc[m-1] += z^m (m = 1..2D), acc[2D+m] += z^m y (m = 0..D) with D-1 multiplies: the high powers are formed
 // inside the accumulating FMA as z^(m-D) * z^D.
 template <int D>
-__device__ __forceinline__ void accumulate_moments_fast(double z, double y, double (&acc)[3 * D + 1]) {
+__device__ __forceinline__ void accumulate_moments_fast(double z, double y, bool with_h, double (&acc)[3 * D + 1]) {
     acc[2 * D] += y;
     if (D == 0) return;
     double p[D + 1];
@@ -105,22 +105,25 @@ __device__ __forceinline__ void accumulate_moments_fast(double z, double y, doub
 #pragma unroll
     for (int m = 2; m <= D; ++m) p[m] = p[m - 1] * z;
 #pragma unroll
-    for (int m = 1; m <= D; ++m) {
-        acc[m - 1] += p[m];
-        acc[2 * D + m] = fma(p[m], y, acc[2 * D + m]);
-        acc[D + m - 1] = fma(p[m], p[D], acc[D + m - 1]);
+    for (int m = 1; m <= D; ++m) acc[2 * D + m] = fma(p[m], y, acc[2 * D + m]);
+    if (with_h) {              // block-uniform: in a contract batch only contract 0 sums the powers of the column
+#pragma unroll
+        for (int m = 1; m <= D; ++m) {
+            acc[m - 1] += p[m];
+            acc[D + m - 1] = fma(p[m], p[D], acc[D + m - 1]);
+        }
     }
 }
 
 template <int D>
 __device__ __forceinline__ bool fast_path_step(const FastConsts& c, const double (&gam)[D + 1], double xd, double xr,
-                                               double& u, double (&acc)[3 * D + 1]) {
+                                               double& u, bool with_h, double (&acc)[3 * D + 1]) {
     const double iv = fma(c.sgn, xd, c.sgnK);
     const double zd = fma(xd, c.da, c.db);
     const double fit = horner<D>(gam, zd);
     const bool ex = (iv > 0.0) && (iv > fit);
     if (ex) u = iv * c.disc;
-    accumulate_moments_fast<D>(fma(xr, c.ra, c.rb), u, acc);
+    accumulate_moments_fast<D>(fma(xr, c.ra, c.rb), u, with_h, acc);
     return ex;
 }
 
@@ -234,6 +237,9 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
     fc.da = a.isg_dec; fc.db = -a.mu_dec * a.isg_dec;
     fc.ra = a.isg_reg; fc.rb = -a.mu_reg * a.isg_reg;
     fc.disc = a.disc_dec;
+    // the power sums of the regressed column are the same for every contract of a batch: contract 0 computes them
+    // (the solve kernel reads them from its rows), the fast path of the others only forms the cross sums with y
+    const bool with_h = !a_in.batch || blockIdx.y == 0;
     constexpr int NK = kTile / 2 / kStepThreads;
     int64_t p0 = p_first;
     int s = 0, s_issue = (kStages - 1) % kStages;
@@ -258,8 +264,8 @@ __global__ void __launch_bounds__(kStepThreads) lsm_step_tma_kernel(const StepAr
                 const V2 vd = sxd[k * kStepThreads], vr = sxr[k * kStepThreads];
                 const U2 uv = su[k * kStepThreads];
                 double2 u = make_double2((double)uv.x, (double)uv.y);
-                bool changed = fast_path_step<D>(fc, gam, (double)vd.x, (double)vr.x, u.x, acc);
-                changed |= fast_path_step<D>(fc, gam, (double)vd.y, (double)vr.y, u.y, acc);
+                bool changed = fast_path_step<D>(fc, gam, (double)vd.x, (double)vr.x, u.x, with_h, acc);
+                changed |= fast_path_step<D>(fc, gam, (double)vd.y, (double)vr.y, u.y, with_h, acc);
                 // the state is written only where a path exercised (one vector store per pair): below maturity most
                 // pairs are untouched, which removes most of the write traffic
                 if (changed) store_state2(up + 2 * k * kStepThreads, u, pol_keep);

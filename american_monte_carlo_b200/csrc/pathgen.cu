@@ -20,9 +20,10 @@ namespace amc {
 
 // ---------------------------------------------------------------------------------------------------------
 // K1, f32 storage: 4 adjacent paths per thread, 4 steps per Philox call and path.  Everything stays on the FP32 /
-// integer / MUFU pipes: the cumulative log-price is a compensated (two-float) sum -- as accurate as a double
-// accumulator rounded to float once per step, without the f32<->f64 conversions and FP64 adds -- and the drift /
-// volatility constants are split into float pairs so no systematic rounding bias enters the drift.
+// integer / MUFU pipes (no f32<->f64 conversions, no FP64 adds): the cumulative log-price is a Kahan-compensated float
+// sum kept in log2 units, so each step costs one FFMA + four FADD for the sum and one MUFU.EX2 + one FMUL for the
+// price.  Accuracy: the compensated sum is good to ~1e-8 in the exponent, below the 6e-8 rounding of the float the
+// price is stored in; the float-rounded step constants (drift, vol) are off by < 3e-8 relative, ~1e-8 on the price.
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -33,20 +34,35 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sin_approx(float x) {
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cos_approx(float x) {
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void __launch_bounds__(256) philox_paths_f32_kernel(float* __restrict__ S, int64_t ld, int n_steps,
                                                                int64_t n_local, int64_t path_offset, GbmParams g,
                                                                uint32_t k0, uint32_t k1) {
     const int64_t n_vec = (n_local + 3) >> 2;
     const float S0f = (float)g.S0;
-    const float dh = (float)g.drift, dl = (float)(g.drift - (double)dh);
-    const float vh = (float)g.vol, vl = (float)(g.vol - (double)vh);
-    const float two_pi = 6.283185307179586f;
+    const float d2 = (float)(g.drift * 1.4426950408889634), v2 = (float)(g.vol * 1.4426950408889634);   // log2 units
     const float neg2ln2 = -1.3862943611198906f;             // -2 ln u = (-2 ln 2) log2 u
+    const float ang_scale = 1.4629180792671596e-09f;        // 2 pi / 2^32
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p0 = v << 2;
-        float Lh[4] = {0.f, 0.f, 0.f, 0.f}, Ll[4] = {0.f, 0.f, 0.f, 0.f};
-        st_stream(reinterpret_cast<float4*>(S + p0), make_float4(S0f, S0f, S0f, S0f));
+        float L[4] = {0.f, 0.f, 0.f, 0.f}, C[4] = {0.f, 0.f, 0.f, 0.f};
+        float* out_col = S + p0;
+        st_stream(reinterpret_cast<float4*>(out_col), make_float4(S0f, S0f, S0f, S0f));
         for (int t0 = 0; t0 < n_steps; t0 += 4) {
             float z[4][4];
 #pragma unroll
@@ -58,32 +74,26 @@ __global__ void __launch_bounds__(256) philox_paths_f32_kernel(float* __restrict
                 for (int h = 0; h < 2; ++h) {
                     // u1 in (0, 1]: full 32-bit resolution in the tail (small integers convert exactly)
                     const float u1 = fmaf((float)r.v[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-                    const float u2 = (float)r.v[2 * h + 1] * 2.3283064365386963e-10f;      // [0, 1]
                     const float rad = sqrt_approx(neg2ln2 * lg2_approx(u1));
-                    const float ang = fmaf(two_pi, u2, -3.14159265358979f);
-                    float sn, cs;
-                    __sincosf(ang, &sn, &cs);
-                    z[i][2 * h] = rad * cs;
-                    z[i][2 * h + 1] = rad * sn;
+                    const float ang = fmaf((float)r.v[2 * h + 1], ang_scale, -3.14159265358979f);   // [-pi, pi]
+                    z[i][2 * h] = rad * cos_approx(ang);
+                    z[i][2 * h + 1] = rad * sin_approx(ang);
                 }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (t0 + j < n_steps) {
+                    out_col += ld;
                     float out[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float gh = fmaf(vh, z[i][j], dh);
-                        const float gl = fmaf(vl, z[i][j], dl);
-                        const float sum = Lh[i] + gh;                       // Knuth two-sum
-                        const float bb = sum - Lh[i];
-                        const float err = (Lh[i] - (sum - bb)) + (gh - bb);
-                        Ll[i] += err + gl;
-                        Lh[i] = sum;
-                        out[i] = S0f * __expf(Lh[i] + Ll[i]);
+                        const float y = fmaf(v2, z[i][j], d2) - C[i];        // Kahan: carry the rounding of the sum
+                        const float t = L[i] + y;
+                        C[i] = (t - L[i]) - y;
+                        L[i] = t;
+                        out[i] = S0f * ex2_approx(t);
                     }
-                    st_stream(reinterpret_cast<float4*>(S + (int64_t)(t0 + j + 1) * ld + p0),
-                              make_float4(out[0], out[1], out[2], out[3]));
+                    st_stream(reinterpret_cast<float4*>(out_col), make_float4(out[0], out[1], out[2], out[3]));
                 }
             }
         }

@@ -181,6 +181,26 @@ def test_philox_paths_statistics_and_price_within_mc_error(amc, golden):
         assert amc.lsm_price(dp3, *price_args(c)).price != res.price
 
 
+def test_philox_f32_log_sum_accuracy(amc):
+    """The float path generator keeps the cumulative log-price as a compensated float sum: with sigma = 0 the path is
+    deterministic, S_t = S0 exp(r t), and must be met to float rounding at every one of 252 steps (no drift of the
+    accumulated sum); with sigma > 0 the mean of S_t must match the forward within Monte Carlo error at the last step."""
+    n = 252
+    dp = amc.generate_asset_paths(36.0, 0.06, 0.0, 1.0, n, 4096, rng="philox", seed=3, dtype="float32")
+    A = np.asarray(dp)
+    want = 36.0 * np.exp(0.06 * np.arange(n + 1) / n)
+    assert np.max(np.abs(A - want[None, :]) / want[None, :]) < 2.5e-7
+    dp.free()
+    P = 2_000_000
+    dq = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, n, P, rng="philox", seed=3, dtype="float32")
+    ST = dq.column(n)
+    fwd = 36.0 * np.exp(0.06)
+    assert abs(ST.mean() - fwd) < 5 * ST.std() / np.sqrt(P)
+    lr = np.log(ST / 36.0)
+    assert abs(lr.mean() - (0.06 - 0.02)) < 5 * 0.2 / np.sqrt(P) and abs(lr.std() - 0.2) < 5 * 0.2 / np.sqrt(2 * P)
+    dq.free()
+
+
 def test_philox_paths_do_not_depend_on_sharding(amc):
     """Counters are GLOBAL path ids: a shard generated with an offset equals the same rows of the full set."""
     import ctypes as C
