@@ -64,6 +64,9 @@ PROTOTYPES = {
     "amc_lsm_price_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LsmSpec), C.c_int, c_double_p, C.c_void_p,
                                       C.POINTER(LsmTiming), C.c_int]),
     "amc_continuation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "amc_ccr_exposures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "amc_percentiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "amc_intrinsic_value": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]),
     "amc_regression_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                      C.c_double, C.c_void_p, C.c_void_p, c_int_p]),

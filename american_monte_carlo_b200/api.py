@@ -430,6 +430,34 @@ def lsmc_option_pricing(paths, K, r, dt, option_type, barrier_level=None,
     return res.price, cont
 
 
+def compute_ccr_exposures(continuation_values):
+    """amc.py:400-414: [(t, PFE_5, PFE_95, EPE)] -- per step the 5th / 95th percentile (numpy's linear rule) and the
+    mean of the finite continuation values.
+
+    Given the lazy `ContinuationValues` of `lsmc_option_pricing` everything stays on the device: the values are
+    recomputed from the stored polynomials and the percentiles found by a radix select (no [n_paths] vector is
+    materialised or sorted).  Any other sequence of (t, S_t, values_t) tuples (amc.py:478 passes QuantLib values)
+    goes through the same select, one host array at a time.
+    """
+    if isinstance(continuation_values, ContinuationValues):
+        cv = continuation_values
+        res = cv._ensure()
+        n = cv._paths.n_time_steps
+        lo, hi, epe = np.empty(n + 1), np.empty(n + 1), np.empty(n + 1)
+        gam = np.ascontiguousarray(res.gamma)
+        N.check(N.lib().amc_ccr_exposures(cv._ctx.handle, cv._paths.handle, gam.ctypes.data, res.degree, 0.05, 0.95,
+                                          lo.ctypes.data, hi.ctypes.data, epe.ctypes.data))
+        return [(t, lo[t], hi[t], epe[t]) for t in range(n + 1)]
+    out = []
+    ctx = default_context()
+    for t, _, cont in continuation_values:
+        vals = np.ascontiguousarray(cont, dtype=np.float64).ravel()
+        r3 = np.empty(3)
+        N.check(N.lib().amc_percentiles(ctx.handle, vals.ctypes.data, vals.size, 0.05, 0.95, r3.ctypes.data))
+        out.append((t, r3[0], r3[1], r3[2]))
+    return out
+
+
 # --------------------------------------------------------------------------------------------- small array ops
 def intrinsic_value(S, K, option_type="Call"):
     """amc.py:85-86, elementwise on the device; returns float64 with the shape of S."""

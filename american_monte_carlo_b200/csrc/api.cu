@@ -105,7 +105,7 @@ struct amc_ctx {
     int* peer_err = nullptr;
     uint32_t peer_seq = 0;
     // grow-only scratch (one pricing call at a time per context)
-    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab;
+    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab, ccr;
     std::vector<cudaEvent_t> events;
     int grid_cache[3][AMC_MAX_K];
     // freed path matrices are kept for reuse (all work is ordered on one stream, so a recycled buffer is safe):
@@ -177,7 +177,7 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
     if (c->mailbox) cudaFree(c->mailbox);
     if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
-    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc, &c->batch_tab};
+    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc, &c->batch_tab, &c->ccr};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf& b : c->path_pool)
@@ -942,6 +942,99 @@ extern "C" int amc_continuation(amc_ctx* c, const amc_paths* p, int t, const dou
     CU(launch_continuation(p->dtype, column(p, t), p->n_local, gam_dev, degree, p->mu[t], 1.0 / p->sigma[t], 1, out_dev,
                            c->stream));
     CU(cudaMemcpyAsync(out, out_dev, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exposures: compute_ccr_exposures, amc.py:400-414
+static int ccr_run(amc_ctx* c, const CcrSource& src, int64_t n_local, bool exchange, double q_lo, double q_hi,
+                   double* out3_dev, SelState* st, unsigned long long* hist, double* partials, int grid) {
+    CU(cudaMemsetAsync(st, 0, sizeof(SelState), c->stream));
+    for (int pass = 0; pass < kSelPasses; ++pass) {
+        CU(launch_ccr_hist(src, n_local, st, pass, hist, partials, grid, c->stream));
+        if (exchange) {        // sharded paths: the histograms (and, once, the partial sums) are global
+            NC(g_nccl.AllReduce(hist, hist, (size_t)kSelTargets * kSelBins, ncclUint64, ncclSum, c->comm, c->stream));
+            if (pass == 0) NC(g_nccl.AllReduce(partials, partials, (size_t)grid, ncclFloat64, ncclSum, c->comm, c->stream));
+        }
+        CU(launch_ccr_scan(st, hist, pass, partials, grid, q_lo, q_hi, out3_dev, c->stream));
+    }
+    return AMC_OK;
+}
+
+static int ccr_scratch(amc_ctx* c, int n_out, int64_t n_local, double** out_dev, SelState** st, unsigned long long** hist,
+                       double** partials, int* grid) {
+    int64_t g = (n_local + 255) / 256;
+    const int64_t cap = (int64_t)c->sm_count * 4;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    if (c->world > 1) g = cap;                     // the same on every rank: the partial sums are all-reduced elementwise
+    *grid = (int)g;
+    const size_t hist_bytes = (size_t)kSelTargets * kSelBins * 8;
+    const size_t bytes = hist_bytes + 256 + (size_t)g * 8 + (size_t)n_out * 3 * 8;
+    int rc = ensure(c->ccr, bytes);
+    if (rc) return rc;
+    char* base = (char*)c->ccr.p;
+    *hist = (unsigned long long*)base;
+    *st = (SelState*)(base + hist_bytes);
+    *partials = (double*)(base + hist_bytes + 256);
+    *out_dev = (double*)(base + hist_bytes + 256 + (size_t)g * 8);
+    static_assert(sizeof(SelState) <= 256, "SelState");
+    CU(cudaMemsetAsync(base, 0, hist_bytes, c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_ccr_exposures(amc_ctx* c, const amc_paths* p, const double* gamma, int degree, double q_lo,
+                                 double q_hi, double* pfe_lo, double* pfe_hi, double* epe) {
+    if (!c || !p || !gamma || !pfe_lo || !pfe_hi || !epe) return fail(AMC_ERR_VALUE, "amc_ccr_exposures: null argument");
+    if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_ccr_exposures: path set belongs to another context");
+    if (degree < 0 || degree > AMC_MAX_DEGREE) return fail(AMC_ERR_VALUE, "degree %d outside 0..%d", degree, AMC_MAX_DEGREE);
+    if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0))
+        return fail(AMC_ERR_VALUE, "Percentiles must be in the range [0, 100]");
+    CU(cudaSetDevice(c->device));
+    const int n = p->n_steps;
+    double* out_dev; SelState* st; unsigned long long* hist; double* partials; int grid;
+    int rc = ccr_scratch(c, n + 1, p->n_local, &out_dev, &st, &hist, &partials, &grid);
+    if (rc) return rc;
+    const bool exchange = c->world > 1 && p->n_global != p->n_local;
+    for (int t = 0; t <= n; ++t) {
+        CcrSource src;
+        memset(&src, 0, sizeof(src));
+        src.x = column(p, t);
+        src.x_f32 = p->dtype == AMC_F32;
+        src.degree = degree;
+        src.clamp = 1;                                  // np.maximum(fit, 0), amc.py:132
+        src.zero = (t == n);                            // amc.py:145: zeros at maturity
+        src.mu = p->mu[t];
+        src.isg = 1.0 / p->sigma[t];
+        for (int i = 0; i <= degree; ++i) src.gam[i] = gamma[(size_t)t * kMaxK + i];
+        if ((rc = ccr_run(c, src, p->n_local, exchange, q_lo, q_hi, out_dev + 3 * t, st, hist, partials, grid))) return rc;
+    }
+    std::vector<double> h((size_t)(n + 1) * 3);
+    CU(cudaMemcpyAsync(h.data(), out_dev, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int t = 0; t <= n; ++t) { pfe_lo[t] = h[3 * t]; pfe_hi[t] = h[3 * t + 1]; epe[t] = h[3 * t + 2]; }
+    return AMC_OK;
+}
+
+extern "C" int amc_percentiles(amc_ctx* c, const double* values, int64_t n, double q_lo, double q_hi, double out3[3]) {
+    if (!c || !out3 || (n > 0 && !values)) return fail(AMC_ERR_VALUE, "amc_percentiles: null argument");
+    if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0))
+        return fail(AMC_ERR_VALUE, "Percentiles must be in the range [0, 100]");
+    CU(cudaSetDevice(c->device));
+    double* out_dev; SelState* st; unsigned long long* hist; double* partials; int grid;
+    const int world_saved = c->world;
+    c->world = 1;                                      // this array only
+    int rc = ccr_scratch(c, 1, n, &out_dev, &st, &hist, &partials, &grid);
+    c->world = world_saved;
+    if (rc) return rc;
+    if ((rc = ensure(c->misc, (size_t)(n > 0 ? n : 1) * 8))) return rc;
+    if (n > 0) CU(cudaMemcpyAsync(c->misc.p, values, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CcrSource src;
+    memset(&src, 0, sizeof(src));
+    src.vals = (const double*)c->misc.p;
+    if ((rc = ccr_run(c, src, n, false, q_lo, q_hi, out_dev, st, hist, partials, grid))) return rc;
+    CU(cudaMemcpyAsync(out3, out_dev, 24, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return AMC_OK;
 }

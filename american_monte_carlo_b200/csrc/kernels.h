@@ -101,6 +101,30 @@ cudaError_t launch_intrinsic(const double* S_dev, int64_t n, double K, int is_pu
 cudaError_t launch_basis_matrix(const double* X_dev, int64_t n, int basis, int degree, double* out_dev,
                                 cudaStream_t s);
 
+// ccr.cu -- exposures (amc.py:400-414): radix select of the percentiles' order statistics + mean of the finite values
+constexpr int kSelTargets = 4;      // floor / floor+1 order statistics of two percentiles
+constexpr int kSelBins = 2048;      // 11 bits per pass
+constexpr int kSelPasses = 6;       // 11 * 5 + 9 = 64 key bits
+struct CcrSource {                  // where the values of one step come from
+    const void* x;                  // path column (continuation value = clamp(poly((x - mu) * isg)))
+    const double* vals;             // or: an explicit array (device)
+    int x_f32, degree, clamp, zero; // zero: all values are 0 (maturity, amc.py:145)
+    double mu, isg;
+    double gam[kMaxK];
+};
+struct SelState {
+    unsigned long long prefix[kSelTargets];   // key bits decided so far (right-aligned)
+    unsigned long long rank[kSelTargets];     // rank among the keys that share the prefix
+    unsigned long long count;                 // finite values
+    double sum;                               // of the finite values
+    double frac[2];                           // numpy's gamma of the two percentiles
+    int bits_done;
+};
+cudaError_t launch_ccr_hist(const CcrSource& s, int64_t n, const SelState* st, int pass, unsigned long long* hist,
+                            double* sum_partials, int grid, cudaStream_t stream);
+cudaError_t launch_ccr_scan(SelState* st, unsigned long long* hist, int pass, const double* sum_partials, int n_partials,
+                            double q_lo, double q_hi, double* out3_dev, cudaStream_t stream);
+
 // pathgen.cu
 struct GbmParams {
     double S0, drift, vol;     // per-step log drift (r - sigma^2/2) dt and vol sigma sqrt(dt)

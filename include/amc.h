@@ -167,6 +167,18 @@ int amc_lsm_price_batch(amc_ctx* ctx, const amc_paths* paths, const amc_lsm_spec
  * per-step copies of amc.py:164).  out: host [n_paths_local]. */
 int amc_continuation(amc_ctx* ctx, const amc_paths* paths, int t, const double* gamma, int degree, double* out);
 
+/* ---- exposures: replaces compute_ccr_exposures, amc.py:400-414 ------------------------------------------------ */
+/* Per step t = 0..n: the q_lo / q_hi quantiles (numpy's default `linear` rule, q in [0, 1]; the reference uses 0.05 and
+ * 0.95) and the mean of the finite continuation values max(fit_t, 0) of ALL paths (global over ranks for a sharded path
+ * set), computed from the stored continuation polynomials `gamma` ([n+1][AMC_MAX_K], as returned in amc_lsm_steps.gamma)
+ * without materialising the [n_paths] vectors; step n is all zeros (amc.py:145).  Outputs: host arrays [n+1]. */
+int amc_ccr_exposures(amc_ctx* ctx, const amc_paths* paths, const double* gamma, int degree, double q_lo, double q_hi,
+                      double* pfe_lo, double* pfe_hi, double* epe);
+/* The same three numbers (q_lo quantile, q_hi quantile, mean of the finite values) for an arbitrary host array:
+ * compute_ccr_exposures on values that did not come from this library (amc.py:478 feeds it QuantLib values).
+ * out3 = NaN, NaN, NaN when no value is finite (amc.py:405-408). */
+int amc_percentiles(amc_ctx* ctx, const double* values, int64_t n, double q_lo, double q_hi, double out3[3]);
+
 /* ---- small array ops kept for API parity (host arrays in, host arrays out, computed on the device) ---- */
 /* intrinsic_value, amc.py:85-86 */
 int amc_intrinsic_value(amc_ctx* ctx, const double* S, int64_t n, double K, int is_put, double* out);

@@ -97,3 +97,24 @@ def test_oracle_matches_reference_when_reference_is_present():
         for m in list(sys.modules):
             if m not in saved:
                 sys.modules.pop(m, None)
+
+
+def test_oracle_ccr_exposures_match_reference_golden():
+    """compute_ccr_exposures (amc.py:400-414): the oracle against tuples produced by the reference itself
+    (tests/golden/make_ccr_golden.py)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ccr_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 3
+    for c in cases:
+        dt = c["T"] / c["n_time_steps"]
+        np.random.seed(c["seed"])
+        paths = orc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], c["n_time_steps"], c["n_paths"])
+        price, cont = orc.lsmc_option_pricing(paths, c["K"], c["r"], dt, c["option_type"], c["barrier_level"],
+                                              c["exercise_type"], c["basis_type"], c["degree"], **c["kwargs"])
+        assert price == c["price"]
+        got = orc.ccr_exposures(cont)
+        assert len(got) == c["n_time_steps"] + 1
+        for (t, a, b, m), want in zip(got, c["exposures"]):
+            assert [t, a, b, m] == want
