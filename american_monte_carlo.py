@@ -5,9 +5,11 @@
 path (amc.py:72-197) runs in libamc.so on the GPU; `get_quantlib_option` is a QuantLib-free benchmark stand-in
 (american_monte_carlo_b200/benchmarks.py); plotting and the notebook driver are out of scope.
 """
-from american_monte_carlo_b200.api import (compute_ccr_exposures, generate_asset_paths, get_basis_polynomials, intrinsic_value,  # noqa: F401
+from american_monte_carlo_b200.api import (apply_exercise, compute_ccr_exposures, estimate_continuation_values,  # noqa: F401
+                                           main, perform_backward_iteration, generate_asset_paths, get_basis_polynomials, intrinsic_value,  # noqa: F401
                                            lsmc_option_pricing, precompute_barrier_hit_matrix, regression_estimate)
 from american_monte_carlo_b200.benchmarks import get_quantlib_option  # noqa: F401
 
-__all__ = ["compute_ccr_exposures", "generate_asset_paths", "get_basis_polynomials", "intrinsic_value", "lsmc_option_pricing",
+__all__ = ["apply_exercise", "compute_ccr_exposures", "estimate_continuation_values", "main",
+           "perform_backward_iteration", "generate_asset_paths", "get_basis_polynomials", "intrinsic_value", "lsmc_option_pricing",
            "precompute_barrier_hit_matrix", "regression_estimate", "get_quantlib_option"]

@@ -61,6 +61,9 @@ PROTOTYPES = {
     "amc_paths_column_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amc_lsm_price": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LsmSpec), c_double_p, C.POINTER(LsmSteps),
                                 C.c_void_p, C.c_void_p, C.POINTER(LsmTiming), C.c_int]),
+    "amc_lsm_price_with_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LsmSpec), C.c_void_p, c_double_p,
+                                          C.POINTER(LsmSteps), C.c_void_p, C.c_void_p, C.POINTER(LsmTiming), C.c_int]),
+    "amc_paths_gather_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "amc_lsm_price_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LsmSpec), C.c_int, c_double_p, C.c_void_p,
                                       C.POINTER(LsmTiming), C.c_int]),
     "amc_continuation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -70,6 +73,10 @@ PROTOTYPES = {
     "amc_intrinsic_value": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]),
     "amc_regression_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                      C.c_double, C.c_void_p, C.c_void_p, c_int_p]),
+    "amc_estimate_continuation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                            C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    "amc_apply_exercise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_int64]),
     "amc_basis_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "amc_barrier_hit_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
 }

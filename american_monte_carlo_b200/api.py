@@ -492,6 +492,132 @@ def regression_estimate(X, Y, basis_type="Power", degree=3, scaling=False, scali
     return out
 
 
+def apply_exercise(cashflows, exercise_times, exercise_value, continuation_estimated, t, indices):
+    """amc.py:90-94: where exercise_value > continuation_estimated (strict) set cashflows / exercise_times at `indices`.
+    Mutates `cashflows` (float64) and `exercise_times` (int64) in place, as the reference does."""
+    if not (isinstance(cashflows, np.ndarray) and cashflows.dtype == np.float64 and cashflows.flags.c_contiguous and
+            isinstance(exercise_times, np.ndarray) and exercise_times.dtype == np.int64 and exercise_times.flags.c_contiguous):
+        raise TypeError("cashflows must be a contiguous float64 ndarray and exercise_times a contiguous int64 ndarray "
+                        "(what lsmc_option_pricing allocates, amc.py:185-186)")
+    ev = np.ascontiguousarray(exercise_value, dtype=np.float64).ravel()
+    ce = np.ascontiguousarray(continuation_estimated, dtype=np.float64).ravel()
+    idx = np.ascontiguousarray(indices, dtype=np.int64).ravel()
+    if not (ev.size == ce.size == idx.size):
+        raise ValueError(f"shape mismatch: {ev.size} exercise values, {ce.size} continuation values, {idx.size} indices")
+    try:
+        N.check(N.lib().amc_apply_exercise(default_context().handle, cashflows.ctypes.data, exercise_times.ctypes.data,
+                                           cashflows.size, ev.ctypes.data, ce.ctypes.data, idx.ctypes.data, idx.size, int(t)))
+    except ValueError as e:                       # numpy raises IndexError for a bad fancy index
+        raise IndexError(str(e)) from None
+
+
+def estimate_continuation_values(paths, t, r, dt, cashflows, exercise_times, basis_type, degree, **kwargs):
+    """amc.py:126-135: regress the discounted cashflows of ALL paths on paths[:, t]; fitted values clamped at zero."""
+    extra = set(kwargs) - {"scaling", "scaling_factor"}
+    if extra:
+        raise TypeError(f"regression_estimate() got an unexpected keyword argument '{sorted(extra)[0]}'")
+    _check_basis(basis_type)
+    X = paths.column(t) if isinstance(paths, DevicePaths) else np.ascontiguousarray(np.asarray(paths)[:, t], dtype=np.float64)
+    cf = np.ascontiguousarray(cashflows, dtype=np.float64).ravel()
+    tau = np.ascontiguousarray(exercise_times, dtype=np.int64).ravel()
+    if not (X.size == cf.size == tau.size):
+        raise ValueError(f"shape mismatch: {X.size} paths, {cf.size} cashflows, {tau.size} exercise times")
+    out = np.empty(X.size)
+    N.check(N.lib().amc_estimate_continuation(default_context().handle, X.ctypes.data, cf.ctypes.data, tau.ctypes.data,
+                                              X.size, int(t), float(r), float(dt), N.BASIS_ID[basis_type], int(degree),
+                                              int(bool(kwargs.get("scaling", False))),
+                                              float(kwargs.get("scaling_factor", 2)), out.ctypes.data))
+    return out
+
+
+def perform_backward_iteration(paths, cashflows, exercise_times, continuation_values, barrier_hit, K, r, dt, option_type,
+                               exercise_type, basis_type, degree, **kwargs):
+    """amc.py:139-167 with the reference's in-place contract: fills `cashflows` (undiscounted, float64) and
+    `exercise_times` (int64), appends one (t, paths[:, t], continuation_t) tuple per step to `continuation_values` and
+    reverses that list (amc.py:164,167).  The whole loop runs as one device sweep.
+
+    Assumes what lsmc_option_pricing passes in (amc.py:185-190): `cashflows` zeros, `exercise_times` full of n, and
+    `barrier_hit` the running-OR matrix of precompute_barrier_hit_matrix (once True, True for all later steps); the
+    latter is checked.  Materialising every step's vectors is O(n_paths x n_steps) host memory, exactly like the
+    reference -- `lsmc_option_pricing` avoids it with a lazy sequence.
+    """
+    extra = set(kwargs) - {"scaling", "scaling_factor"}
+    if extra:
+        raise TypeError(f"regression_estimate() got an unexpected keyword argument '{sorted(extra)[0]}'")
+    ctx = default_context()
+    dp, temporary = _as_device_paths(paths, ctx)
+    try:
+        n, P = dp.n_time_steps, dp.n_paths_local
+        hit = np.asarray(barrier_hit, dtype=bool)
+        if hit.shape != (P, n + 1):
+            raise ValueError(f"barrier_hit must have shape {(P, n + 1)}, got {hit.shape}")
+        if n >= 1 and not np.all(hit[:, 1:] >= hit[:, :-1]):
+            raise NotImplementedError("barrier_hit must be a running OR over time (precompute_barrier_hit_matrix)")
+        first = np.where(hit.any(axis=1), hit.argmax(axis=1), n + 1).astype(np.int32)
+        if n >= 1:
+            _check_basis(basis_type)
+        spec = N.LsmSpec(K=float(K), r=float(r), dt=float(dt), barrier=float("nan"),
+                         scaling_factor=float(kwargs.get("scaling_factor", 2)), is_put=int(option_type == "Put"),
+                         is_american=int(exercise_type == "American"), basis=N.BASIS_ID.get(basis_type, 0),
+                         degree=int(degree), scaling=int(bool(kwargs.get("scaling", False))), want_regression=1,
+                         want_exercise_steps=1, want_svd=0, state_f32=0)
+        rows = n + 1
+        gamma = np.zeros((rows, N.AMC_MAX_K))
+        steps = N.LsmSteps(gamma=gamma.ctypes.data_as(N.c_double_p), beta=None, sv=None, mean_x=None, std_x=None, rank=None)
+        price = C.c_double()
+        tau32 = np.empty(P, dtype=np.int32)
+        N.check(N.lib().amc_lsm_price_with_hits(ctx.handle, dp.handle, C.byref(spec), first.ctypes.data, C.byref(price),
+                                                C.byref(steps), tau32.ctypes.data, None, None, 0))
+        # undiscounted cashflow = payoff at the path's own exercise step where it had knocked in by then (amc.py:93,148)
+        s_tau = np.empty(P)
+        N.check(N.lib().amc_paths_gather_steps(dp.handle, tau32.ctypes.data, s_tau.ctypes.data))
+        pay = intrinsic_value(s_tau, K, option_type)
+        cashflows[...] = np.where(first <= tau32, pay, 0.0)
+        exercise_times[...] = tau32
+        for t in reversed(range(n + 1)):                                               # amc.py:141,164
+            S_t = dp.column(t)
+            if t == n:
+                cont = np.zeros(P)                                                     # amc.py:145
+            else:
+                cont = np.empty(P)
+                g = np.ascontiguousarray(gamma[t])
+                N.check(N.lib().amc_continuation(ctx.handle, dp.handle, t, g.ctypes.data, int(degree), cont.ctypes.data))
+            continuation_values.append((t, S_t, cont))
+        continuation_values.reverse()                                                  # amc.py:167
+    finally:
+        if temporary:
+            dp.free()
+
+
+def main(params):
+    """amc.py:443-503, the computational part: paths -> LSMC price and exposures -> benchmark price -> the same three
+    printed lines.  The per-grid-point QuantLib values (amc.py:474, O(n_paths x n_steps) QuantLib calls) and the plots
+    are presentation and out of scope; returns what was computed."""
+    from .benchmarks import get_quantlib_option
+    S0, K, T, r, sigma = params["S0"], params["K"], params["T"], params["r"], params["sigma"]
+    n_time_steps, n_paths = params["n_time_steps"], params["n_paths"]
+    option_type, exercise_type, barrier_level = params["option_type"], params["exercise_type"], params["barrier_level"]
+    paths = generate_asset_paths(S0, r, sigma, T, n_time_steps, n_paths)                              # amc.py:465
+    dt = T / n_time_steps
+    lsmc_price, continuation_values = lsmc_option_pricing(paths, K, r, dt, option_type, barrier_level, exercise_type,
+                                                          params["basis_type"], params["degree"],
+                                                          scaling=params["scaling"],
+                                                          scaling_factor=params["scaling_factor"])   # amc.py:469-471
+    lsmc_ccr_exposures = compute_ccr_exposures(continuation_values)                                   # amc.py:479
+    benchmark = get_quantlib_option(S0, K, r, T, sigma, n_time_steps, option_type, exercise_type, barrier_level)
+    option_description = f"{exercise_type} {option_type}"
+    barrier_text = f"with Barrier at {barrier_level}" if barrier_level else "without Barrier"
+    print(f"{option_description} Option Price {barrier_text} (LSMC): {lsmc_price:.4f}")               # amc.py:499
+    print(f"{option_description} Option Price {barrier_text} (QuantLib): {benchmark.NPV():.4f}")
+    out = dict(lsmc_price=float(lsmc_price), benchmark_price=float(benchmark.NPV()), lsmc_ccr_exposures=lsmc_ccr_exposures,
+               continuation_values=continuation_values, paths=paths)
+    if barrier_level:
+        plain = get_quantlib_option(S0, K, r, T, sigma, n_time_steps, option_type, exercise_type)
+        print(f"{option_description} Option Price without Barrier (QuantLib): {plain.NPV():.4f}")
+        out["benchmark_price_without_barrier"] = float(plain.NPV())
+    return out
+
+
 def precompute_barrier_hit_matrix(paths, barrier_level):
     """amc.py:171-176: bool [n_paths, n_time_steps+1]."""
     ctx = default_context()

@@ -638,7 +638,7 @@ struct EventPool {
 // read from HBM once per step for the whole batch and the per-step launch chain is paid once.
 static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, int C, double* price,
                      amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out, double* gamma_batch_out,
-                     amc_lsm_timing* timing, int profile) {
+                     amc_lsm_timing* timing, int profile, const int32_t* first_hit_host = nullptr) {
     const amc_lsm_spec* spec = specs;
     int rc;
     CU(cudaSetDevice(c->device));
@@ -649,7 +649,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     bool american = false;
     for (int i = 0; i < C; ++i) american = american || specs[i].is_american != 0;
     const bool regress = (american || spec->want_regression) && n >= 1;
-    const bool barrier = !isnan(spec->barrier);
+    const bool barrier = !isnan(spec->barrier) || first_hit_host != nullptr;
     const int sf32 = spec->state_f32 ? 1 : 0;
     const size_t bU = sf32 ? 4 : 8;
     int grid = step_grid(c, dtype, sf32, D, P);
@@ -694,7 +694,9 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
 
     int32_t* tau = spec->want_exercise_steps ? (int32_t*)c->tau.p : nullptr;
     int32_t* fh = barrier ? (int32_t*)c->first_hit.p : nullptr;
-    if (barrier && P > 0)
+    if (first_hit_host && P > 0)
+        CU(cudaMemcpyAsync(fh, first_hit_host, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+    else if (barrier && P > 0)
         CU(launch_first_hit(dtype, p->S, p->ld, n + 1, P, spec->barrier, fh, c->stream));
 
     // L2 management knob (on by default; AMC_L2_REVERSE=0 for A/B measurements)
@@ -897,6 +899,36 @@ extern "C" int amc_lsm_price(amc_ctx* c, const amc_paths* p, const amc_lsm_spec*
     return lsm_sweep(c, p, spec, 1, price, steps, exercise_step_out, cashflow0_out, nullptr, timing, profile);
 }
 
+extern "C" int amc_lsm_price_with_hits(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* spec,
+                                       const int32_t* first_hit, double* price, amc_lsm_steps* steps,
+                                       int32_t* exercise_step_out, double* cashflow0_out, amc_lsm_timing* timing,
+                                       int profile) {
+    if (!c || !p || !price) return fail(AMC_ERR_VALUE, "amc_lsm_price_with_hits: null argument");
+    if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_lsm_price_with_hits: path set belongs to another context");
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    if (exercise_step_out && !spec->want_exercise_steps)
+        return fail(AMC_ERR_VALUE, "exercise_step_out needs spec.want_exercise_steps");
+    if (spec->state_f32 && p->dtype != AMC_F32) return fail(AMC_ERR_VALUE, "state_f32 needs a float32 path set");
+    return lsm_sweep(c, p, spec, 1, price, steps, exercise_step_out, cashflow0_out, nullptr, timing, profile, first_hit);
+}
+
+extern "C" int amc_paths_gather_steps(const amc_paths* p, const int32_t* steps, double* out) {
+    if (!p || !steps || !out) return fail(AMC_ERR_VALUE, "amc_paths_gather_steps: null argument");
+    if (p->n_local == 0) return AMC_OK;
+    amc_ctx* c = p->ctx;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure(c->misc, (size_t)p->n_local * 12);
+    if (rc) return rc;
+    double* out_dev = (double*)c->misc.p;
+    int32_t* st_dev = (int32_t*)(out_dev + p->n_local);
+    CU(cudaMemcpyAsync(st_dev, steps, (size_t)p->n_local * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_gather_steps(p->dtype, p->S, p->ld, p->n_steps + 1, p->n_local, st_dev, out_dev, c->stream));
+    CU(cudaMemcpyAsync(out, out_dev, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
 extern "C" int amc_lsm_price_batch(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, int n_contracts,
                                    double* prices, double* gamma_out, amc_lsm_timing* timing, int profile) {
     if (!c || !p || !prices || !specs) return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: null argument");
@@ -1074,9 +1106,11 @@ extern "C" int amc_basis_matrix(amc_ctx* c, const double* X, int64_t n, int basi
     return AMC_OK;
 }
 
-extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, int64_t n, int basis, int degree,
-                                  int scaling, double scaling_factor, double* fitted, double* beta, int* rank) {
-    if (!c || (n > 0 && (!X || !Y || !fitted))) return fail(AMC_ERR_VALUE, "amc_regression_fit: null argument");
+// Y either comes from the host (Y) or is produced on the device by `prepare_y` (writes n doubles at c->U.p)
+template <typename PrepareY>
+static int regression_fit_impl(amc_ctx* c, const double* X, const double* Y, PrepareY prepare_y, int64_t n, int basis,
+                               int degree, int scaling, double scaling_factor, int clamp, double* fitted, double* beta,
+                               int* rank) {
     amc_lsm_spec sp;
     memset(&sp, 0, sizeof(sp));
     sp.basis = basis;
@@ -1101,8 +1135,12 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     if ((rc = ensure(c->U, (size_t)ldp * 8)) || (rc = ensure(c->partials, (size_t)grid * kAccStride * 8)) ||
         (rc = ensure(c->sums, kAccStride * 8)) || (rc = ensure(c->diag, (4 * kMaxK + 8) * 8)))
         return cleanup(rc);
-    e = cudaMemcpyAsync(c->U.p, Y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "H2D Y: %s", cudaGetErrorString(e)));
+    if (Y) {
+        e = cudaMemcpyAsync(c->U.p, Y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "H2D Y: %s", cudaGetErrorString(e)));
+    } else if ((rc = prepare_y((double*)c->U.p))) {
+        return cleanup(rc);
+    }
     double* dg = (double*)c->diag.p;
     StepArgs a;
     memset(&a, 0, sizeof(a));
@@ -1142,7 +1180,7 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     e = launch_solve(s, c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "solve kernel: %s", cudaGetErrorString(e)));
     if ((rc = ensure(c->misc, (size_t)n * 8))) return cleanup(rc);
-    e = launch_continuation(AMC_F64, px->S, n, dg, degree, px->mu[0], a.isg_reg, 0, (double*)c->misc.p, c->stream);
+    e = launch_continuation(AMC_F64, px->S, n, dg, degree, px->mu[0], a.isg_reg, clamp, (double*)c->misc.p, c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "fit kernel: %s", cudaGetErrorString(e)));
     double small[3 * kMaxK + 4];
     cudaMemcpyAsync(fitted, c->misc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
@@ -1152,6 +1190,61 @@ extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, 
     if (beta) memcpy(beta, small + kMaxK, (size_t)(degree + 1) * 8);
     if (rank) memcpy(rank, small + 3 * kMaxK + 2, 4);
     return cleanup(AMC_OK);
+}
+
+extern "C" int amc_regression_fit(amc_ctx* c, const double* X, const double* Y, int64_t n, int basis, int degree,
+                                  int scaling, double scaling_factor, double* fitted, double* beta, int* rank) {
+    if (!c || (n > 0 && (!X || !Y || !fitted))) return fail(AMC_ERR_VALUE, "amc_regression_fit: null argument");
+    return regression_fit_impl(c, X, Y, [](double*) { return (int)AMC_OK; }, n, basis, degree, scaling, scaling_factor, 0,
+                               fitted, beta, rank);
+}
+
+extern "C" int amc_estimate_continuation(amc_ctx* c, const double* X, const double* cashflows,
+                                         const int64_t* exercise_times, int64_t n, int64_t t, double r, double dt, int basis,
+                                         int degree, int scaling, double scaling_factor, double* out) {
+    if (!c || (n > 0 && (!X || !cashflows || !exercise_times || !out)))
+        return fail(AMC_ERR_VALUE, "amc_estimate_continuation: null argument");
+    auto prepare = [&](double* y_dev) -> int {
+        // Y = cashflows * exp(-r dt (tau - t)), amc.py:128, formed on the device
+        int rc = ensure(c->stage, (size_t)n * 16);
+        if (rc) return rc;
+        double* cf_dev = (double*)c->stage.p;
+        int64_t* tau_dev = (int64_t*)(cf_dev + n);
+        CU(cudaMemcpyAsync(cf_dev, cashflows, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(tau_dev, exercise_times, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(launch_discount(cf_dev, tau_dev, n, t, r, dt, y_dev, c->stream));
+        return AMC_OK;
+    };
+    return regression_fit_impl(c, X, nullptr, prepare, n, basis, degree, scaling, scaling_factor, 1, out, nullptr, nullptr);
+}
+
+extern "C" int amc_apply_exercise(amc_ctx* c, double* cashflows, int64_t* exercise_times, int64_t n_total,
+                                  const double* exercise_value, const double* continuation, const int64_t* indices,
+                                  int64_t m, int64_t t) {
+    if (!c || (n_total > 0 && (!cashflows || !exercise_times)) || (m > 0 && (!exercise_value || !continuation || !indices)))
+        return fail(AMC_ERR_VALUE, "amc_apply_exercise: null argument");
+    if (m <= 0 || n_total <= 0) return AMC_OK;
+    for (int64_t i = 0; i < m; ++i)
+        if (indices[i] < 0 || indices[i] >= n_total)
+            return fail(AMC_ERR_VALUE, "index %lld is out of bounds for axis 0 with size %lld", (long long)indices[i], (long long)n_total);
+    CU(cudaSetDevice(c->device));
+    int rc = ensure(c->misc, (size_t)n_total * 16 + (size_t)m * 24);
+    if (rc) return rc;
+    double* cf_dev = (double*)c->misc.p;
+    int64_t* tau_dev = (int64_t*)(cf_dev + n_total);
+    double* ev_dev = (double*)(tau_dev + n_total);
+    double* ce_dev = ev_dev + m;
+    int64_t* idx_dev = (int64_t*)(ce_dev + m);
+    CU(cudaMemcpyAsync(cf_dev, cashflows, (size_t)n_total * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(tau_dev, exercise_times, (size_t)n_total * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ev_dev, exercise_value, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ce_dev, continuation, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(idx_dev, indices, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_apply_exercise(cf_dev, tau_dev, ev_dev, ce_dev, idx_dev, m, t, c->stream));
+    CU(cudaMemcpyAsync(cashflows, cf_dev, (size_t)n_total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(exercise_times, tau_dev, (size_t)n_total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
 }
 
 extern "C" int amc_barrier_hit_matrix(amc_ctx* c, const amc_paths* p, double barrier, uint8_t* out) {

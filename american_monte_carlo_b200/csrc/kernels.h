@@ -97,6 +97,10 @@ cudaError_t launch_step(int dtype, int state_f32, int degree, int grid, const St
 cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl = false);
 cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const double* gamma_dev, int degree, double mu,
                                 double isg, int clamp, double* out_dev, cudaStream_t s);
+cudaError_t launch_discount(const double* cf_dev, const int64_t* tau_dev, int64_t n, int64_t t, double r, double dt,
+                            double* y_dev, cudaStream_t s);
+cudaError_t launch_apply_exercise(double* cf_dev, int64_t* tau_dev, const double* ev_dev, const double* cont_dev,
+                                  const int64_t* idx_dev, int64_t m, int64_t t, cudaStream_t s);
 cudaError_t launch_intrinsic(const double* S_dev, int64_t n, double K, int is_put, double* out_dev, cudaStream_t s);
 cudaError_t launch_basis_matrix(const double* X_dev, int64_t n, int basis, int degree, double* out_dev,
                                 cudaStream_t s);
@@ -137,6 +141,8 @@ cudaError_t launch_transpose_in(int dtype, const double* S_rowmajor_dev, void* S
                                 int64_t n_local, cudaStream_t s);
 cudaError_t launch_gather_rows(int dtype, const void* S, int64_t ld, int n_cols, int64_t p0, int64_t p1,
                                double* out_dev, cudaStream_t s);
+cudaError_t launch_gather_steps(int dtype, const void* S, int64_t ld, int n_cols, int64_t n, const int32_t* steps_dev,
+                                double* out_dev, cudaStream_t s);
 cudaError_t launch_column_to_f64(int dtype, const void* col, int64_t n, double* out_dev, cudaStream_t s);
 // shifted one-pass column statistics: partial[(col * n_chunks + chunk) * 2 + {0,1}] = sum(x - c), sum((x - c)^2)
 // with c = first element of the column

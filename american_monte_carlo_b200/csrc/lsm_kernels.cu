@@ -187,6 +187,26 @@ __global__ void basis_matrix_kernel(const double* __restrict__ X, int64_t n, int
     }
 }
 
+// Regression target of estimate_continuation_values (amc.py:128): Y = cashflows * exp(-r dt (tau - t)).
+__global__ void discount_kernel(const double* __restrict__ cf, const int64_t* __restrict__ tau, int64_t n, int64_t t,
+                                double r, double dt, double* __restrict__ y) {
+    const double mrdt = -r * dt;                       // the reference's expression order: (-r * dt) * (tau - t)
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+        y[p] = cf[p] * exp(mrdt * (double)(tau[p] - t));
+}
+
+// apply_exercise (amc.py:90-94): where exercise_value > continuation (strict), scatter value and step.
+__global__ void apply_exercise_kernel(double* __restrict__ cf, int64_t* __restrict__ tau, const double* __restrict__ ev,
+                                      const double* __restrict__ cont, const int64_t* __restrict__ idx, int64_t m,
+                                      int64_t t) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        if (ev[i] > cont[i]) {
+            cf[idx[i]] = ev[i];
+            tau[idx[i]] = t;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // launchers
 // dtype: storage of the path matrix (0 = f64, 1 = f32); state_f32: per-path state stored as float (f32 paths only)
@@ -235,6 +255,18 @@ cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const doubl
         continuation_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, gamma_dev, degree, mu, isg, clamp, out_dev);
     else
         continuation_kernel<double><<<grid, 256, 0, s>>>((const double*)x, n, gamma_dev, degree, mu, isg, clamp, out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_discount(const double* cf_dev, const int64_t* tau_dev, int64_t n, int64_t t, double r, double dt,
+                            double* y_dev, cudaStream_t s) {
+    discount_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, s>>>(cf_dev, tau_dev, n, t, r, dt, y_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_exercise(double* cf_dev, int64_t* tau_dev, const double* ev_dev, const double* cont_dev,
+                                  const int64_t* idx_dev, int64_t m, int64_t t, cudaStream_t s) {
+    apply_exercise_kernel<<<blocks_for(m, 256, 148 * 8), 256, 0, s>>>(cf_dev, tau_dev, ev_dev, cont_dev, idx_dev, m, t);
     return cudaGetLastError();
 }
 

@@ -309,6 +309,29 @@ cudaError_t launch_gather_rows(int dtype, const void* S, int64_t ld, int n_cols,
     return cudaGetLastError();
 }
 
+// out[p] = S[steps[p]][p]: each path's value at its own step (e.g. its exercise step)
+template <typename XT>
+__global__ void gather_steps_kernel(const XT* __restrict__ S, int64_t ld, int n_cols, int64_t n,
+                                    const int32_t* __restrict__ steps, double* __restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        int t = steps[p];
+        t = t < 0 ? 0 : (t >= n_cols ? n_cols - 1 : t);
+        out[p] = (double)S[(int64_t)t * ld + p];
+    }
+}
+
+cudaError_t launch_gather_steps(int dtype, const void* S, int64_t ld, int n_cols, int64_t n, const int32_t* steps_dev,
+                                double* out_dev, cudaStream_t s) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    if (dtype == 1)
+        gather_steps_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)S, ld, n_cols, n, steps_dev, out_dev);
+    else
+        gather_steps_kernel<double><<<(int)blocks, 256, 0, s>>>((const double*)S, ld, n_cols, n, steps_dev, out_dev);
+    return cudaGetLastError();
+}
+
 template <typename XT>
 __global__ void column_to_f64_kernel(const XT* __restrict__ col, int64_t n, double* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

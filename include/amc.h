@@ -151,6 +151,16 @@ int amc_lsm_price(amc_ctx* ctx, const amc_paths* paths, const amc_lsm_spec* spec
                   amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out,
                   amc_lsm_timing* timing, int profile);
 
+/* amc_lsm_price with the knock-in information supplied by the caller instead of a barrier level: first_hit[p] = first
+ * step at which path p counts as knocked in (n_time_steps+1 = never) -- the running-OR matrix that
+ * perform_backward_iteration (amc.py:139-167) receives, as one index per path.  spec->barrier is ignored. */
+int amc_lsm_price_with_hits(amc_ctx* ctx, const amc_paths* paths, const amc_lsm_spec* spec, const int32_t* first_hit,
+                            double* price, amc_lsm_steps* steps, int32_t* exercise_step_out, double* cashflow0_out,
+                            amc_lsm_timing* timing, int profile);
+/* out[p] = S[p, steps[p]] (host arrays, [n_paths_local]): e.g. each path's price at its exercise step, from which the
+ * undiscounted cashflows of amc.py:93,148 follow exactly. */
+int amc_paths_gather_steps(const amc_paths* paths, const int32_t* steps, double* out);
+
 /* Price `n_contracts` contracts on ONE device-resident path set in the same launches (BASELINE.json config 4: the
  * strike axis of a strike x vol x maturity grid shares its paths; the reference re-simulates and re-prices per
  * contract in a Python loop, american_monte_carlo_additional_plots.py:100-107).  The contracts may differ in K,
@@ -185,6 +195,16 @@ int amc_intrinsic_value(amc_ctx* ctx, const double* S, int64_t n, double K, int 
 /* regression_estimate, amc.py:110-122: fitted values of the (possibly rank-truncated) least-squares fit */
 int amc_regression_fit(amc_ctx* ctx, const double* X, const double* Y, int64_t n, int basis, int degree,
                        int scaling, double scaling_factor, double* fitted, double* beta, int* rank);
+/* estimate_continuation_values, amc.py:126-135, on host arrays: Y = cashflows * exp(-r dt (exercise_times - t)) is formed
+ * on the device, regressed on X (= paths[:, t]) and the fitted values are clamped at zero (amc.py:132) */
+int amc_estimate_continuation(amc_ctx* ctx, const double* X, const double* cashflows, const int64_t* exercise_times,
+                              int64_t n, int64_t t, double r, double dt, int basis, int degree, int scaling,
+                              double scaling_factor, double* out);
+/* apply_exercise, amc.py:90-94: for i < m with exercise_value[i] > continuation[i] (strict) set
+ * cashflows[indices[i]] = exercise_value[i] and exercise_times[indices[i]] = t; both arrays ([n_total]) are updated in place */
+int amc_apply_exercise(amc_ctx* ctx, double* cashflows, int64_t* exercise_times, int64_t n_total,
+                       const double* exercise_value, const double* continuation, const int64_t* indices, int64_t m,
+                       int64_t t);
 /* get_basis_polynomials, amc.py:98-106: out is [n][degree+1] row-major */
 int amc_basis_matrix(amc_ctx* ctx, const double* X, int64_t n, int basis, int degree, double* out);
 /* precompute_barrier_hit_matrix, amc.py:171-176: out is [n_paths][n_time_steps+1] row-major bytes (0/1) */
