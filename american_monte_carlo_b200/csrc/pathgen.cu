@@ -57,7 +57,6 @@ __global__ void __launch_bounds__(256) philox_paths_f32_kernel(float* __restrict
     const float S0f = (float)g.S0;
     const float d2 = (float)(g.drift * 1.4426950408889634), v2 = (float)(g.vol * 1.4426950408889634);   // log2 units
     const float neg2ln2 = -1.3862943611198906f;             // -2 ln u = (-2 ln 2) log2 u
-    const float ang_scale = 1.4629180792671596e-09f;        // 2 pi / 2^32
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p0 = v << 2;
         float L[4] = {0.f, 0.f, 0.f, 0.f}, C[4] = {0.f, 0.f, 0.f, 0.f};
@@ -75,7 +74,10 @@ __global__ void __launch_bounds__(256) philox_paths_f32_kernel(float* __restrict
                     // u1 in (0, 1]: full 32-bit resolution in the tail (small integers convert exactly)
                     const float u1 = fmaf((float)r.v[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
                     const float rad = sqrt_approx(neg2ln2 * lg2_approx(u1));
-                    const float ang = fmaf((float)r.v[2 * h + 1], ang_scale, -3.14159265358979f);   // [-pi, pi]
+                    // angle: the low 23 bits become the mantissa of a float in [1, 2) (one LOP3, no int->float
+                    // conversion on the MUFU pipe); 2 pi f - 3 pi lies in [-pi, pi)
+                    const float f12 = __uint_as_float((r.v[2 * h + 1] & 0x007fffffu) | 0x3f800000u);
+                    const float ang = fmaf(f12, 6.283185307179586f, -9.42477796076938f);
                     z[i][2 * h] = rad * cos_approx(ang);
                     z[i][2 * h + 1] = rad * sin_approx(ang);
                 }

@@ -58,6 +58,23 @@ def main():
         out["philox"] = dict(multi=float(rq.price), single=float(rs.price),
                              gamma_max_rel=float(np.max(np.abs(gam_multi - rs.gamma) / (np.abs(rs.gamma) + 1e-300))))
         ds.free()
+    # (2b) exposures (amc.py:400-414) of the sharded set: histograms all-reduced -> same percentiles as one GPU
+    from american_monte_carlo_b200.api import ContinuationValues
+    pargs = ((K, r, T / n, "Put", None, "American", "Power", 3), {})
+    dq2 = amc.generate_asset_paths(S0, r, sigma, T, n, Pp, rng="philox", seed=11, dtype="float32", ctx=ctx)
+    rq2 = amc.lsm_price(dq2, *pargs[0], want_regression=True, ctx=ctx)
+    ex_multi = amc.compute_ccr_exposures(ContinuationValues(dq2, False, pargs, rq2, ctx))
+    if rank == 0:
+        solo2 = amc.Context(local)
+        ds2 = amc.generate_asset_paths(S0, r, sigma, T, n, Pp, rng="philox", seed=11, dtype="float32", ctx=solo2)
+        rs2 = amc.lsm_price(ds2, *pargs[0], want_regression=True, ctx=solo2)
+        ex_solo = amc.compute_ccr_exposures(ContinuationValues(ds2, False, pargs, rs2, solo2))
+        scale = max(abs(e[2]) for e in ex_solo) + 1e-12
+        out["exposures"] = dict(
+            max_pct_diff=float(max(max(abs(a[1] - b[1]), abs(a[2] - b[2])) for a, b in zip(ex_multi, ex_solo)) / scale),
+            max_mean_diff=float(max(abs(a[3] - b[3]) for a, b in zip(ex_multi, ex_solo)) / scale), steps=len(ex_multi))
+        ds2.free()
+    dq2.free()
     # every rank must hold the same polynomial (the regression is global)
     g = torch.tensor(gam_multi, device="cuda")
     gmax, gmin = g.clone(), g.clone()

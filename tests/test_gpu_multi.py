@@ -40,6 +40,8 @@ def test_sharded_sweep_equals_single_gpu_and_oracle(libamc_path, allreduce):
     assert abs(ph["multi"] - ph["single"]) <= 1e-11 * ph["single"]
     assert ph["gamma_max_rel"] < 1e-9
     assert out["gamma_identical_across_ranks"]
+    ex = out["exposures"]                       # the polynomials differ at the 1e-9 level between 1 and N GPUs
+    assert ex["steps"] == 51 and ex["max_pct_diff"] < 1e-8 and ex["max_mean_diff"] < 1e-8
     ad = out["adopted"]
     assert abs(ad["price"] - inj["oracle"]) <= 1e-10 * inj["oracle"]
     assert ad["mu_err"] < 1e-12 and ad["sg_err"] < 1e-10
