@@ -111,6 +111,9 @@ struct amc_ctx {
     // freed path matrices are kept for reuse (all work is ordered on one stream, so a recycled buffer is safe):
     // a pricing loop then never pays cudaMalloc/cudaFree (both synchronise the device) for multi-GB matrices
     std::vector<DevBuf> path_pool;
+    // CUDA graph of the last sweep's launch chain (replayed when the next sweep would enqueue identical launches)
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_key, graph_seen;
 };
 constexpr size_t kPathPoolMax = 2;
 
@@ -182,6 +185,7 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
         if (b->p) cudaFree(b->p);
     for (DevBuf& b : c->path_pool)
         if (b.p) cudaFree(b.p);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -730,8 +734,40 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     sspec.scaling_factor = spec->scaling_factor;
     sspec.n_paths = Pg;
 
+    // Launch-bound sweeps (small path sets: two launches per ~7 us step) are replayed as a CUDA graph: the launches of
+    // a sweep are first written into a plan; if the plan is byte-identical to the previous sweep's (same buffers, same
+    // contract, same path-set geometry) the instantiated graph of that sweep is launched instead of 2(n+1) kernels.
+    // The first occurrence of a plan runs eagerly, the second is captured, later ones are replayed.
+    struct PlanItem { int kind, pdl; StepArgs a; SolveArgs s; };
+    static const int opt_graph = getenv("AMC_GRAPH") ? atoi(getenv("AMC_GRAPH")) : 1;
+    const bool planned = opt_graph && !profile && !exchange;
+    std::vector<PlanItem> plan;
+    auto emit_step = [&](const StepArgs& a, bool pdl_flag) -> int {
+        if (planned) {
+            plan.emplace_back();
+            PlanItem& it = plan.back();
+            memset(&it, 0, sizeof(it));
+            it.kind = 0; it.pdl = pdl_flag; it.a = a;
+            return AMC_OK;
+        }
+        CU(launch_step(dtype, sf32, D, grid, a, c->stream, pdl_flag, C));
+        return AMC_OK;
+    };
+    auto emit_solve = [&](const SolveArgs& s, bool pdl_flag) -> int {
+        if (planned) {
+            plan.emplace_back();
+            PlanItem& it = plan.back();
+            memset(&it, 0, sizeof(it));
+            it.kind = 1; it.pdl = pdl_flag; it.s = s;
+            return AMC_OK;
+        }
+        CU(launch_solve(s, c->stream, pdl_flag));
+        return AMC_OK;
+    };
+
     auto run_step = [&](int t, int mode, bool moments) -> int {
         StepArgs a;
+        memset(&a, 0, sizeof(a));
         a.x_dec = (mode != kObserve) ? column(p, t) : nullptr;
         a.x_reg = moments ? column(p, t - 1) : nullptr;
         a.U = c->U.p;
@@ -756,7 +792,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         a.coef_stride = (int64_t)nrow * kMaxK;
         int r2;
         if ((r2 = bracket(step_ev))) return r2;
-        CU(launch_step(dtype, sf32, D, grid, a, c->stream, pdl && n_step > 0, C));
+        if ((r2 = emit_step(a, pdl && n_step > 0))) return r2;
         if ((r2 = bracket(step_ev))) return r2;
         ++n_step;
         return AMC_OK;
@@ -764,6 +800,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
 
     auto run_solve = [&](int t_reg, bool final_price) -> int {
         SolveArgs s;
+        memset(&s, 0, sizeof(s));
         s.partials = (const double*)c->partials.p;
         s.n_rows = grid;
         s.sums = (double*)c->sums.p;
@@ -795,7 +832,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
                 if (s.peer.seq == 0) s.peer.seq = ++c->peer_seq;      // 0 is the "empty cell" value
                 s.peer.err = c->peer_err;
             }
-            CU(launch_solve(s, c->stream, pdl));
+            if ((r2 = emit_solve(s, pdl))) return r2;
             ++n_solve;
         } else {
             s.do_reduce = 1; s.do_solve = 0;
@@ -821,6 +858,49 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
             const int mode = (t == n) ? kMaturity : (american ? kDecide : kObserve);
             if ((rc = run_step(t, mode, t > 0))) return rc;
             if ((rc = run_solve(t - 1, t == 0))) return rc;
+        }
+    }
+    if (planned) {
+        auto enqueue_plan = [&]() -> int {
+            for (const PlanItem& it : plan) {
+                if (it.kind == 0) CU(launch_step(dtype, sf32, D, grid, it.a, c->stream, it.pdl != 0, C));
+                else CU(launch_solve(it.s, c->stream, it.pdl != 0));
+            }
+            return AMC_OK;
+        };
+        const int hdr[6] = {dtype, sf32, D, grid, C, (int)plan.size()};
+        std::vector<unsigned char> key(sizeof(hdr) + plan.size() * sizeof(PlanItem));
+        memcpy(key.data(), hdr, sizeof(hdr));
+        if (!plan.empty()) memcpy(key.data() + sizeof(hdr), plan.data(), plan.size() * sizeof(PlanItem));
+        bool done = false;
+        if (c->graph_exec && key == c->graph_key) {
+            CU(cudaGraphLaunch(c->graph_exec, c->stream));
+            done = true;
+        } else if (key == c->graph_seen) {
+            // second identical sweep: capture it (a failed capture falls back to plain launches)
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ge = nullptr;
+            bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = enqueue_plan() == AMC_OK;
+                ok = (cudaStreamEndCapture(c->stream, &g) == cudaSuccess) && ok && g;
+            }
+            if (ok) ok = cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (ok) {
+                if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+                c->graph_exec = ge;
+                c->graph_key = key;
+                CU(cudaGraphLaunch(c->graph_exec, c->stream));
+                done = true;
+            } else {
+                cudaGetLastError();
+                c->graph_seen.clear();
+            }
+        }
+        if (!done) {
+            c->graph_seen = key;
+            if ((rc = enqueue_plan())) return rc;
         }
     }
     CU(cudaEventRecord(ev_stop, c->stream));

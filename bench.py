@@ -333,7 +333,8 @@ def main():
     from american_monte_carlo_b200 import _native as N
     import ctypes as C
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # not the legacy default stream: the sweep's launch chain is
+    torch.cuda.set_stream(stream)                   # replayed as a CUDA graph, which needs a capturable stream
     ctx = amc.Context(local_rank, stream=stream.cuda_stream)
     amc.set_default_context(ctx)
     if world > 1:

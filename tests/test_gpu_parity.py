@@ -372,3 +372,23 @@ def test_batch_argument_errors(amc):
     solo = amc.lsm_price(dp, 40.0, 0.06, 0.2, "Put", None, "American", "Power", 3)
     assert one[0] == solo.price
     dp.free()
+
+
+def test_repeated_sweeps_replay_a_graph_with_identical_results(amc):
+    """The launch chain of a sweep is captured into a CUDA graph on its second identical occurrence and replayed
+    afterwards (api.cu); every occurrence must give the same bits, and a different contract in between must not be
+    served by the stale graph."""
+    dp = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 20, 30_000, rng="philox", seed=5)
+    args = (40.0, 0.06, 0.05, "Put", None, "American", "Power", 3)
+    prices = [amc.lsm_price(dp, *args).price for _ in range(5)]
+    assert len(set(prices)) == 1
+    other = amc.lsm_price(dp, 42.0, *args[1:]).price
+    assert other != prices[0]
+    again = [amc.lsm_price(dp, *args).price for _ in range(3)]
+    assert set(again) == {prices[0]}
+    batch = [amc.lsm_price_batch(dp, [(40.0, "Put", "American"), (42.0, "Put", "American")], 0.06, 0.05, None, "Power", 3)
+             for _ in range(4)]
+    for b in batch[1:]:
+        np.testing.assert_array_equal(b, batch[0])
+    assert abs(batch[0][0] - prices[0]) <= 1e-12 * prices[0] and abs(batch[0][1] - other) <= 1e-12 * other
+    dp.free()
