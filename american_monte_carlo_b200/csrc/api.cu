@@ -103,7 +103,6 @@ struct amc_ctx {
     void* mailbox = nullptr;
     void* peer_mailbox[kPeerMax] = {};
     int* peer_err = nullptr;
-    uint32_t peer_seq = 0;
     // grow-only scratch (one pricing call at a time per context)
     DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab, ccr;
     std::vector<cudaEvent_t> events;
@@ -264,7 +263,6 @@ static int peer_setup(amc_ctx* c) {
     if ((int)(flag + 0.5) != W)
         return fail(AMC_ERR_NCCL, "%d of %d ranks could map all mailboxes%s%s", (int)(flag + 0.5), W, why[0] ? "; " : "", why);
     c->transport = 2;
-    c->peer_seq = 0;
     return AMC_OK;
 }
 
@@ -740,7 +738,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     // The first occurrence of a plan runs eagerly, the second is captured, later ones are replayed.
     struct PlanItem { int kind, pdl; StepArgs a; SolveArgs s; };
     static const int opt_graph = getenv("AMC_GRAPH") ? atoi(getenv("AMC_GRAPH")) : 1;
-    const bool planned = opt_graph && !profile && !exchange;
+    const bool planned = opt_graph && !profile && (!exchange || c->transport == 2);
     std::vector<PlanItem> plan;
     auto emit_step = [&](const StepArgs& a, bool pdl_flag) -> int {
         if (planned) {
@@ -828,8 +826,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
                 for (int q = 0; q < c->world; ++q) s.peer.mailbox[q] = (uint4*)c->peer_mailbox[q];
                 s.peer.world = c->world;
                 s.peer.rank = c->rank;
-                s.peer.seq = ++c->peer_seq;
-                if (s.peer.seq == 0) s.peer.seq = ++c->peer_seq;      // 0 is the "empty cell" value
+                s.peer.seq_ctr = (uint32_t*)(c->peer_err + 16);        // same 256-byte block as the error flag
                 s.peer.err = c->peer_err;
             }
             if ((r2 = emit_solve(s, pdl))) return r2;

@@ -64,7 +64,9 @@ constexpr int kPeerRing = 4;
 struct PeerArgs {
     uint4* mailbox[kPeerMax] = {};  // mailbox[q] = rank q's mailbox mapped into this process (cudaIpc); [rank] = own
     int world = 0, rank = 0;        // world <= 1: no exchange
-    uint32_t seq = 0;               // sequence number of this all-reduce (never 0), same on every rank
+    uint32_t* seq_ctr = nullptr;    // device counter: every all-reduce takes the next sequence number (never 0); all
+                                    // ranks run the same chain of solve launches, so the numbers agree -- and the launch
+                                    // arguments stay constant from sweep to sweep (CUDA-graph replay)
     int* err = nullptr;             // device flag: set to 1 if a peer did not show up in time
 };
 

@@ -85,7 +85,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
     if (a.peer.world > 1) {
         // fused all-reduce over peer memory: push this rank's sums into everybody's mailbox, then gather
         const int W = a.peer.world;
-        const uint32_t seq = a.peer.seq;
+        __shared__ uint32_t s_seq;
+        if (threadIdx.x == 0) {
+            uint32_t v = atomicAdd(a.peer.seq_ctr, 1u) + 1u;
+            if (v == 0u) v = atomicAdd(a.peer.seq_ctr, 1u) + 1u;      // 0 marks a never-written cell
+            s_seq = v;
+        }
+        __syncthreads();
+        const uint32_t seq = s_seq;
         const int slot = (int)(seq % kPeerRing);
         for (int idx = threadIdx.x; idx < W * nacc; idx += kSolveThreads) {
             const int q = idx / nacc, i = idx - q * nacc;
