@@ -494,7 +494,7 @@ def main():
                        else "amc_paths_generate + amc_lsm_price"},
         "gpu_launches": int(args.steps * (1 + tm["step_launches"] + tm["solve_launches"])),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "lsm_step_kernel (fused exercise decision + regression moments)",
+        "roofline": {"bound": "hbm", "kernel": "lsm_step_tma_kernel (fused exercise decision + regression moments)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / step_launches,
                      "launches_per_sweep": step_launches, "avg_launch_ms": step_ms / step_launches,
