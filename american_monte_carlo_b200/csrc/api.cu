@@ -442,7 +442,7 @@ extern "C" int amc_paths_from_normals_dev(amc_ctx* c, const double* Z_dev, doubl
 }
 
 // measured maps for adopted matrices: per-column (count, mean, M2), merged over chunks and ranks in fixed order
-static int measured_maps(amc_ctx* c, amc_paths* p) {
+static int measured_maps(amc_ctx* c, amc_paths* p, bool across_ranks = true) {
     const int ncol = p->n_steps + 1;
     const int n_chunks = 64;
     std::vector<double> cnt(ncol, 0.0), mean(ncol, 0.0), m2(ncol, 0.0);
@@ -471,7 +471,7 @@ static int measured_maps(amc_ctx* c, amc_paths* p) {
             m2[t] = var * n;
         }
     }
-    if (c->world > 1) {
+    if (c->world > 1 && across_ranks) {
         // all-gather (count, mean, M2) triples and merge in rank order (Chan et al. pairwise update)
         const size_t per = (size_t)ncol * 3;
         int rc = ensure(c->misc, per * 8 * (size_t)(c->world + 1));
@@ -1071,13 +1071,13 @@ static int ccr_run(amc_ctx* c, const CcrSource& src, int64_t n_local, bool excha
     return AMC_OK;
 }
 
-static int ccr_scratch(amc_ctx* c, int n_out, int64_t n_local, double** out_dev, SelState** st, unsigned long long** hist,
-                       double** partials, int* grid) {
+static int ccr_scratch(amc_ctx* c, int n_out, int64_t n_local, bool across_ranks, double** out_dev, SelState** st,
+                       unsigned long long** hist, double** partials, int* grid) {
     int64_t g = (n_local + 255) / 256;
     const int64_t cap = (int64_t)c->sm_count * 4;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    if (c->world > 1) g = cap;                     // the same on every rank: the partial sums are all-reduced elementwise
+    if (c->world > 1 && across_ranks) g = cap;     // the same on every rank: the partial sums are all-reduced elementwise
     *grid = (int)g;
     const size_t hist_bytes = (size_t)kSelTargets * kSelBins * 8;
     const size_t bytes = hist_bytes + 256 + (size_t)g * 8 + (size_t)n_out * 3 * 8;
@@ -1103,9 +1103,9 @@ extern "C" int amc_ccr_exposures(amc_ctx* c, const amc_paths* p, const double* g
     CU(cudaSetDevice(c->device));
     const int n = p->n_steps;
     double* out_dev; SelState* st; unsigned long long* hist; double* partials; int grid;
-    int rc = ccr_scratch(c, n + 1, p->n_local, &out_dev, &st, &hist, &partials, &grid);
-    if (rc) return rc;
     const bool exchange = c->world > 1 && p->n_global != p->n_local;
+    int rc = ccr_scratch(c, n + 1, p->n_local, exchange, &out_dev, &st, &hist, &partials, &grid);
+    if (rc) return rc;
     for (int t = 0; t <= n; ++t) {
         CcrSource src;
         memset(&src, 0, sizeof(src));
@@ -1132,10 +1132,7 @@ extern "C" int amc_percentiles(amc_ctx* c, const double* values, int64_t n, doub
         return fail(AMC_ERR_VALUE, "Percentiles must be in the range [0, 100]");
     CU(cudaSetDevice(c->device));
     double* out_dev; SelState* st; unsigned long long* hist; double* partials; int grid;
-    const int world_saved = c->world;
-    c->world = 1;                                      // this array only
-    int rc = ccr_scratch(c, 1, n, &out_dev, &st, &hist, &partials, &grid);
-    c->world = world_saved;
+    int rc = ccr_scratch(c, 1, n, false, &out_dev, &st, &hist, &partials, &grid);       // this array only
     if (rc) return rc;
     if ((rc = ensure(c->misc, (size_t)(n > 0 ? n : 1) * 8))) return rc;
     if (n > 0) CU(cudaMemcpyAsync(c->misc.p, values, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1202,10 +1199,7 @@ static int regression_fit_impl(amc_ctx* c, const double* X, const double* Y, Pre
     auto cleanup = [&](int code) { amc_paths_free(px); return code; };
     cudaError_t e = cudaMemcpyAsync(px->S, X, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "H2D X: %s", cudaGetErrorString(e)));
-    const int world_saved = c->world;
-    c->world = 1;                                   // statistics of THIS array only
-    rc = measured_maps(c, px);
-    c->world = world_saved;
+    rc = measured_maps(c, px, false);               // statistics of THIS array only
     if (rc) return cleanup(rc);
     const int grid = step_grid(c, AMC_F64, 0, degree, n);
     const int64_t ldp = padded_len(n);

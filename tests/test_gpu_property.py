@@ -1,0 +1,47 @@
+"""GPU tier: property test (hypothesis, derandomised) -- random small contracts through the CUDA path must take the same
+exercise decisions as the oracle and give the same price (1e-10), for every basis, degree 0..3, both payoff sides,
+both exercise styles, with and without barrier / scaling, ragged path counts and 1..9 time steps."""
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import lsm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+_AMC = {}
+
+
+@pytest.fixture(autouse=True)
+def _bind(amc):
+    _AMC["m"] = amc
+
+
+contract = st.fixed_dictionaries(dict(
+    seed=st.integers(0, 2 ** 20), P=st.integers(60, 700), n=st.integers(1, 9),
+    S0=st.sampled_from([20.0, 36.0, 100.0]), moneyness=st.floats(0.8, 1.2), r=st.floats(0.0, 0.08),
+    sigma=st.floats(0.05, 0.5), T=st.sampled_from([0.25, 1.0, 2.0]), opt=st.sampled_from(["Put", "Call"]),
+    ex=st.sampled_from(["American", "European"]), barrier=st.sampled_from([None, 0.7, 0.9]),
+    basis=st.sampled_from(["Power", "Chebyshev", "Legendre"]), degree=st.integers(0, 3), scaling=st.booleans()))
+
+
+@settings(max_examples=60, deadline=None, derandomize=True)
+@given(contract)
+def test_random_small_contracts_match_the_oracle(c):
+    amc = _AMC["m"]
+    np.random.seed(c["seed"])
+    Z = orc.draw_normals(c["P"], c["n"])
+    paths = orc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    K = c["S0"] * c["moneyness"]
+    barrier = None if c["barrier"] is None else c["S0"] * c["barrier"]
+    kw = dict(scaling=True) if c["scaling"] else {}
+    dt = c["T"] / c["n"]
+    want = orc.lsm_backward(paths, K, c["r"], dt, c["opt"], barrier, c["ex"], c["basis"], c["degree"],
+                            keep_continuation=False, **kw)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    got = amc.lsm_price(dp, K, c["r"], dt, c["opt"], barrier, c["ex"], c["basis"], c["degree"], want_exercise_steps=True, **kw)
+    dp.free()
+    flips = int((got.exercise_steps != want.exercise_times).sum())
+    assert flips == 0, (c, flips)
+    assert abs(got.price - want.price) <= 1e-10 * max(abs(want.price), 1e-6), (c, got.price, want.price)
