@@ -731,6 +731,8 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     sspec.want_svd = spec->want_svd;
     sspec.scaling_factor = spec->scaling_factor;
     sspec.n_paths = Pg;
+    static const int opt_warp_solve = getenv("AMC_WARP_SOLVE") ? atoi(getenv("AMC_WARP_SOLVE")) : -1;
+    sspec.warp_solve = opt_warp_solve < 0 ? (D >= 6) : opt_warp_solve;    // scalar registers win up to k = 6
 
     // Launch-bound sweeps (small path sets: two launches per ~7 us step) are replayed as a CUDA graph: the launches of
     // a sweep are first written into a plan; if the plan is byte-identical to the previous sweep's (same buffers, same

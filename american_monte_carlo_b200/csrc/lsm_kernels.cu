@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.cuh"
+#include "lsm_solve_warp.cuh"
 
 namespace amc {
 
@@ -122,12 +123,17 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
         }
         __syncthreads();
     }
-    if (threadIdx.x != 0) return;
     if (a.final_price) {
-        a.price[0] = part[0][2 * d] / a.spec.n_paths;
+        if (threadIdx.x == 0) a.price[0] = part[0][2 * d] / a.spec.n_paths;
         return;
     }
-    if (!a.do_solve) return;
+    if (!a.do_solve || threadIdx.x >= 32) return;
+    // warp 0: cooperative solve of the certified full-rank case; everything else (degenerate column, rank truncation,
+    // SVD diagnostics) falls through to the scalar routine on thread 0
+    __shared__ SolveShared<K> solve_sh;
+    const bool solved = lsm_solve_warp<K>(a.spec, &part[0][0], &part[0][2 * d], a.y_scale, a.mu_ref, a.sigma_ref, solve_sh,
+                                          a.gamma, a.beta, a.sv, a.mean_std, a.rank);
+    if (solved || threadIdx.x != 0) return;
     double h[2 * d + 1], g[K];
     h[0] = a.spec.n_paths;
 #pragma unroll

@@ -50,6 +50,7 @@ struct SolveSpec {
     int want_svd;             // always run the SVD and report singular values (diagnostics / tests)
     double scaling_factor;    // regression_estimate(..., scaling_factor=2)
     double n_paths;           // GLOBAL number of paths (all ranks) -- enters numpy's rcond = eps*max(P,k)
+    int warp_solve;           // device only: try the warp-cooperative routine first (lsm_solve_warp.cuh)
 };
 
 struct SolveResult {

@@ -1,0 +1,194 @@
+// Warp-cooperative version of the per-step regression solve for the common case: full internal rank and full rank of
+// the user's design matrix certified (see lsm_solve.h for the method and the scalar routine that handles everything
+// else -- degenerate columns, rank truncation through the Jacobi SVD, want_svd diagnostics).
+//
+// One warp, lane i owns row / column i of the k x k matrices, which live in shared memory.  Every element is computed
+// by exactly the expression (and operation order) the scalar routine uses, so the two give the same bits; only the two
+// Frobenius norms of the certificate are summed in a different order, which can matter for the certificate's yes/no
+// within rounding of its 0.2 % margin and never for the coefficients.  The point is latency: the scalar solve keeps its
+// matrices in registers up to k = 6 and spills beyond (19 us per step at degree 8); here the dependent chain is the
+// Cholesky's k square-root/reciprocal pairs plus O(k^2) multiply-adds per lane (~3 us at degree 8).
+#pragma once
+#include "lsm_solve.h"
+
+namespace amc {
+
+template <int K>
+struct SolveShared {
+    double Hn[2 * K];
+    double L[K][K + 1], M[K][K + 1], B[K][K + 1], Bi[K][K + 1];
+    double w[K], Linv[K], dinv[K], gamma[K], beta[K];
+};
+
+// Returns true when the step was solved here (outputs written by lane 0); false -> run the scalar routine.
+template <int K>
+__device__ bool lsm_solve_warp(const SolveSpec& spec, const double* hsum /* [2d]: sum z^m, m = 1..2d */,
+                               const double* gsum /* [d+1]: sum z^m y */, double y_scale, double mu_ref, double sigma_ref,
+                               SolveShared<K>& sh, double* gamma_out, double* beta_out, double* sv_out,
+                               double* mean_std_out, int* rank_out) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int D = K - 1;
+    const int lane = threadIdx.x & 31;
+    if (spec.want_svd || D == 0 || !spec.warp_solve) return false;
+    const double P = spec.n_paths;
+    const double invP = 1.0 / P;
+    for (int m = lane; m <= 2 * D; m += 32) sh.Hn[m] = (m == 0 ? P : hsum[m - 1]) * invP;
+    const double bi = (lane < K) ? gsum[lane] * y_scale * invP : 0.0;
+    __syncwarp();
+
+    const double mz = sh.Hn[1];
+    double vz = sh.Hn[2] - mz * mz;
+    if (vz < 0.0) vz = 0.0;
+    const double mean_x = mu_ref + sigma_ref * mz;
+    const double std_x = sigma_ref * sqrt(vz);
+
+    // Cholesky G = L L^T of the Hankel Gram (lsm_solve.h, same expressions)
+    for (int i = lane; i < K * (K + 1); i += 32) (&sh.L[0][0])[i] = 0.0;
+    __syncwarp();
+    const double pivot_tol = 2e-14;
+    for (int j = 0; j < K; ++j) {
+        double inv = 0.0;
+        int ok = 1;
+        if (lane == j) {
+            double djj = sh.Hn[2 * j];
+            for (int c = 0; c < j; ++c) djj -= sh.L[j][c] * sh.L[j][c];
+            if (!(djj > pivot_tol * sh.Hn[2 * j])) {
+                ok = 0;
+            } else {
+                const double ljj = sqrt(djj);
+                inv = 1.0 / ljj;
+                sh.L[j][j] = ljj;
+                sh.Linv[j] = inv;
+            }
+        }
+        ok = __shfl_sync(FULL, ok, j);
+        if (!ok) return false;                               // numerically dependent monomial: scalar routine
+        inv = __shfl_sync(FULL, inv, j);
+        if (lane > j && lane < K) {
+            double v = sh.Hn[lane + j];
+            for (int c = 0; c < j; ++c) v -= sh.L[lane][c] * sh.L[j][c];
+            sh.L[lane][j] = v * inv;
+        }
+        __syncwarp();
+    }
+
+    // w = L^-1 b: lane i carries v_i; after w_c is known every later row subtracts L[i][c] w_c (ascending c, as scalar)
+    double v = bi;
+    for (int c = 0; c < K; ++c) {
+        double wc = (lane == c) ? v * sh.Linv[c] : 0.0;
+        wc = __shfl_sync(FULL, wc, c);
+        if (lane == c) sh.w[c] = wc;
+        if (lane > c && lane < K) v -= sh.L[lane][c] * wc;
+    }
+
+    // change of basis for the user's polynomials, u = ca + cb z (lsm_solve.h build_change_of_basis, column by column)
+    double ca, cb;
+    if (spec.scaling) {
+        const double sdev = std_x > 1e-6 ? std_x : 1e-6;
+        const double den = spec.scaling_factor * sdev;
+        ca = (mu_ref - mean_x) / den;
+        cb = sigma_ref / den;
+    } else {
+        ca = mu_ref;
+        cb = sigma_ref;
+    }
+    for (int i = lane; i < K * (K + 1); i += 32) (&sh.M[0][0])[i] = 0.0;
+    __syncwarp();
+    if (lane == 0) sh.M[0][0] = 1.0;
+    __syncwarp();
+    for (int j = 1; j < K; ++j) {
+        if (lane <= j) {
+            const int i = lane;
+            const double um = ca * ((i < j) ? sh.M[i][j - 1] : 0.0) + ((i > 0) ? cb * sh.M[i - 1][j - 1] : 0.0);
+            const double p1 = (i < j) ? sh.M[i][j - 1] : 0.0;
+            const double p2 = (j >= 2 && i <= j - 2) ? sh.M[i][j - 2] : 0.0;
+            double val;
+            switch (spec.basis) {
+                case kChebyshev: val = (j == 1) ? um : 2.0 * um - p2; break;
+                case kLegendre: val = ((2.0 * j - 1.0) * um - (j - 1.0) * p2) / (double)j; break;
+                case kLaguerre: val = ((2.0 * j - 1.0) * p1 - um - (j - 1.0) * p2) / (double)j; break;
+                default: val = um;
+            }
+            sh.M[i][j] = val;
+        }
+        __syncwarp();
+    }
+
+    // B = L^T M (upper triangular): lane j forms column j
+    if (lane < K) {
+        const int j = lane;
+        for (int i = 0; i < K; ++i) {
+            double s = 0.0;
+            for (int l = 0; l < K; ++l)
+                if (l >= i && l <= j) s += sh.L[l][i] * sh.M[l][j];
+            sh.B[i][j] = s;
+        }
+    }
+    __syncwarp();
+
+    // full-rank certificate: s_min >= 1/|B^-1|_F, s_max <= |B|_F; lane j inverts column j by back substitution
+    const double eps = 2.220446049250313e-16;
+    const double rcond = eps * (P > (double)K ? P : (double)K);
+    int okd = 1;
+    if (lane < K) {
+        okd = (sh.B[lane][lane] != 0.0);
+        sh.dinv[lane] = 1.0 / sh.B[lane][lane];
+    }
+    okd = __all_sync(FULL, okd);
+    __syncwarp();
+    double nb = 0.0, nbi = 0.0;
+    if (lane < K) {
+        const int j = lane;
+        for (int i = 0; i < K; ++i) sh.Bi[i][j] = 0.0;
+        sh.Bi[j][j] = sh.dinv[j];
+        for (int i = K - 1; i >= 0; --i) {
+            if (i < j) {
+                double s = 0.0;
+                for (int l = 0; l < K; ++l)
+                    if (l > i && l <= j) s += sh.B[i][l] * sh.Bi[l][j];
+                sh.Bi[i][j] = -s * sh.dinv[i];
+            }
+        }
+        for (int i = 0; i <= j; ++i) {
+            nb += sh.B[i][j] * sh.B[i][j];
+            nbi += sh.Bi[i][j] * sh.Bi[i][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nb += __shfl_xor_sync(FULL, nb, o);
+        nbi += __shfl_xor_sync(FULL, nbi, o);
+    }
+    const bool certified = okd && (nb == nb) && (nbi == nbi) && (1.0 > 1.002 * rcond * rcond * nb * nbi);
+    if (!certified) return false;                            // rank decision needs the SVD: scalar routine
+    __syncwarp();
+
+    // beta = B^-1 w (numpy's coefficients in the user's basis); gamma = L^-T w by back substitution (lane 0, scalar order)
+    if (lane < K) {
+        double s = 0.0;
+        for (int l = 0; l < K; ++l)
+            if (l >= lane) s += sh.Bi[lane][l] * sh.w[l];
+        sh.beta[lane] = s;
+    }
+    if (lane == 0) {
+        for (int i = K - 1; i >= 0; --i) {
+            double s = sh.w[i];
+            for (int c = 0; c < K; ++c)
+                if (c > i) s -= sh.L[c][i] * sh.gamma[c];
+            sh.gamma[i] = s * sh.Linv[i];
+        }
+    }
+    __syncwarp();
+    if (lane < kMaxK) {
+        gamma_out[lane] = lane < K ? sh.gamma[lane] : 0.0;
+        if (beta_out) beta_out[lane] = lane < K ? sh.beta[lane] : 0.0;
+        if (sv_out) sv_out[lane] = 0.0;
+    }
+    if (lane == 0) {
+        if (mean_std_out) { mean_std_out[0] = mean_x; mean_std_out[1] = std_x; }
+        if (rank_out) rank_out[0] = K;
+    }
+    return true;
+}
+
+}  // namespace amc
