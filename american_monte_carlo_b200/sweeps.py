@@ -98,6 +98,11 @@ def default_contract_grid():
     return strikes, vols, maturities
 
 
+def cells_of_rank(n_cells, world_size, rank):
+    """(vol, maturity) cells priced by `rank`: round-robin, so every rank gets a mix of short and long maturities."""
+    return [i for i in range(int(n_cells)) if i % int(world_size) == int(rank)]
+
+
 def contract_grid(S0, r, strikes, vols, maturities, n_time_steps, n_paths, option_type="Put",
                   exercise_type="American", barrier_level=None, basis_type="Power", degree=3, scaling=False,
                   scaling_factor=2, *, seed=42, dtype="float32", ctx: Context | None = None, combine=True,
@@ -115,10 +120,11 @@ def contract_grid(S0, r, strikes, vols, maturities, n_time_steps, n_paths, optio
     maturities = np.asarray(maturities, dtype=float)
     prices = np.zeros((len(strikes), len(vols), len(maturities)))
     world, rank = ctx.world_size, ctx.rank
+    mine_cells = set(cells_of_rank(len(vols) * len(maturities), world, rank))
     cell = 0
     for iv, sigma in enumerate(vols):
         for im, T in enumerate(maturities):
-            mine = (cell % world) == rank
+            mine = cell in mine_cells
             cell += 1
             if not mine:
                 continue
