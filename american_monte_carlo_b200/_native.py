@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libamc.so")
+LIB_PATH = os.environ.get("AMC_LIBAMC") or os.path.join(HERE, "libamc.so")    # override: A/B of two builds
 
 AMC_MAX_K = 11
 F64, F32 = 0, 1
