@@ -110,6 +110,10 @@ struct amc_ctx {
     // freed path matrices are kept for reuse (all work is ordered on one stream, so a recycled buffer is safe):
     // a pricing loop then never pays cudaMalloc/cudaFree (both synchronise the device) for multi-GB matrices
     std::vector<DevBuf> path_pool;
+    // host -> device streaming of injected normals: a copy stream and two staging halves, so that the H2D copy of
+    // chunk k+1 overlaps the path kernel of chunk k (and the staging buffer is 2 chunks, not the whole array)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_ready = nullptr;
     // CUDA graph of the last sweep's launch chain (replayed when the next sweep would enqueue identical launches)
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<unsigned char> graph_key, graph_seen;
@@ -185,6 +189,12 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
     for (DevBuf& b : c->path_pool)
         if (b.p) cudaFree(b.p);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -403,6 +413,45 @@ extern "C" int amc_paths_generate(amc_ctx* c, double S0, double r, double sigma,
     return AMC_OK;
 }
 
+// Host normals -> paths, pipelined: chunks of whole paths go through two staging halves; the copy stream moves chunk
+// k+1 over PCIe while the path kernel turns chunk k into prices on the context stream.
+static int stream_normals_from_host(amc_ctx* c, amc_paths* p, const double* Z, GbmParams g) {
+    const int n = p->n_steps;
+    const int64_t P = p->n_local;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    }
+    const size_t row_bytes = (size_t)n * 8;
+    int64_t chunk = (int64_t)((256u << 20) / row_bytes) / 128 * 128;      // ~256 MB, a multiple of the kernel's 128-path block
+    if (chunk < 128) chunk = 128;
+    if (chunk > P) chunk = P;
+    const size_t chunk_bytes = ((size_t)chunk * row_bytes + 255) / 256 * 256;
+    int rc = ensure(c->stage, 2 * chunk_bytes);
+    if (rc) return rc;
+    // the staging halves may still be read by kernels queued earlier on the context stream
+    CU(cudaEventRecord(c->ev_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
+    const size_t es = elem_size(p->dtype);
+    int k = 0;
+    for (int64_t p0 = 0; p0 < P; p0 += chunk, ++k) {
+        const int buf = k & 1;
+        const int64_t np = (P - p0 < chunk) ? (P - p0) : chunk;
+        double* st = (double*)((char*)c->stage.p + (size_t)buf * chunk_bytes);
+        if (k >= 2) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[buf], 0));
+        CU(cudaMemcpyAsync(st, Z + (size_t)p0 * n, (size_t)np * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
+        CU(launch_from_normals(p->dtype, st, (char*)p->S + (size_t)p0 * es, p->ld, n, np, g, c->stream));
+        CU(cudaEventRecord(c->ev_free[buf], c->stream));
+    }
+    return AMC_OK;
+}
+
 static int from_normals_impl(amc_ctx* c, const double* Z, bool z_on_device, double S0, double r, double sigma, double T,
                              int n_time_steps, int64_t n_local, int64_t n_global, int dtype, amc_paths** out) {
     if (n_time_steps < 1) return fail(AMC_ERR_VALUE, "n_time_steps must be >= 1");
@@ -410,19 +459,13 @@ static int from_normals_impl(amc_ctx* c, const double* Z, bool z_on_device, doub
     amc_paths* p = nullptr;
     int rc = paths_alloc(c, n_time_steps, n_local, n_global, dtype, &p);
     if (rc) return rc;
-    if (n_local > 0) {
-        const double* Zd = Z;
-        if (!z_on_device) {
-            const size_t zb = (size_t)n_local * (size_t)n_time_steps * 8;
-            rc = ensure(c->stage, zb);
-            if (rc) { amc_paths_free(p); return rc; }
-            cudaError_t e = cudaMemcpyAsync(c->stage.p, Z, zb, cudaMemcpyHostToDevice, c->stream);
-            if (e != cudaSuccess) { amc_paths_free(p); return fail(AMC_ERR_CUDA, "H2D of normals: %s", cudaGetErrorString(e)); }
-            Zd = (const double*)c->stage.p;
-        }
-        cudaError_t e = launch_from_normals(dtype, Zd, p->S, p->ld, n_time_steps, n_local,
+    if (n_local > 0 && z_on_device) {
+        cudaError_t e = launch_from_normals(dtype, Z, p->S, p->ld, n_time_steps, n_local,
                                             gbm_params(S0, r, sigma, T, n_time_steps), c->stream);
         if (e != cudaSuccess) { amc_paths_free(p); return fail(AMC_ERR_CUDA, "normals path kernel launch: %s", cudaGetErrorString(e)); }
+    } else if (n_local > 0) {
+        rc = stream_normals_from_host(c, p, Z, gbm_params(S0, r, sigma, T, n_time_steps));
+        if (rc) { amc_paths_free(p); return rc; }
     }
     analytic_maps(p, S0, r, sigma, T);
     *out = p;
