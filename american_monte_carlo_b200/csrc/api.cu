@@ -415,8 +415,11 @@ extern "C" int amc_paths_generate(amc_ctx* c, double S0, double r, double sigma,
 
 // Host normals -> paths, pipelined: chunks of whole paths go through two staging halves; the copy stream moves chunk
 // k+1 over PCIe while the path kernel turns chunk k into prices on the context stream.
-static int stream_normals_from_host(amc_ctx* c, amc_paths* p, const double* Z, GbmParams g) {
-    const int n = p->n_steps;
+// `row_doubles` doubles per path in the host array; `consume(staged_chunk, first_path, n_paths)` launches the kernel that
+// turns a staged chunk into columns.
+template <typename Consume>
+static int stream_rows_from_host(amc_ctx* c, amc_paths* p, const double* Z, int row_doubles, Consume consume) {
+    const int n = row_doubles;
     const int64_t P = p->n_local;
     if (!c->copy_stream) {
         CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -427,7 +430,9 @@ static int stream_normals_from_host(amc_ctx* c, amc_paths* p, const double* Z, G
         CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     }
     const size_t row_bytes = (size_t)n * 8;
-    int64_t chunk = (int64_t)((256u << 20) / row_bytes) / 128 * 128;      // ~256 MB, a multiple of the kernel's 128-path block
+    const char* mb_env = getenv("AMC_STAGE_CHUNK_MB");                       // tests shrink it to force many chunks
+    const size_t mb = (mb_env && atoi(mb_env) > 0) ? (size_t)atoi(mb_env) : 256;
+    int64_t chunk = (int64_t)((mb << 20) / row_bytes) / 128 * 128;           // a multiple of the kernels' 128-path blocks
     if (chunk < 128) chunk = 128;
     if (chunk > P) chunk = P;
     const size_t chunk_bytes = ((size_t)chunk * row_bytes + 255) / 256 * 256;
@@ -446,10 +451,16 @@ static int stream_normals_from_host(amc_ctx* c, amc_paths* p, const double* Z, G
         CU(cudaMemcpyAsync(st, Z + (size_t)p0 * n, (size_t)np * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
         CU(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
-        CU(launch_from_normals(p->dtype, st, (char*)p->S + (size_t)p0 * es, p->ld, n, np, g, c->stream));
+        CU(consume(st, (char*)p->S + (size_t)p0 * es, np));
         CU(cudaEventRecord(c->ev_free[buf], c->stream));
     }
     return AMC_OK;
+}
+
+static int stream_normals_from_host(amc_ctx* c, amc_paths* p, const double* Z, GbmParams g) {
+    return stream_rows_from_host(c, p, Z, p->n_steps, [&](const double* st, void* S0p, int64_t np) {
+        return launch_from_normals(p->dtype, st, S0p, p->ld, p->n_steps, np, g, c->stream);
+    });
 }
 
 static int from_normals_impl(amc_ctx* c, const double* Z, bool z_on_device, double S0, double r, double sigma, double T,
@@ -556,13 +567,11 @@ extern "C" int amc_paths_from_host(amc_ctx* c, const double* S, int n_time_steps
     int rc = paths_alloc(c, n_time_steps, n_paths_local, n_paths_global, dtype, &p);
     if (rc) return rc;
     if (n_paths_local > 0) {
-        const size_t sb = (size_t)n_paths_local * (size_t)(n_time_steps + 1) * 8;
-        rc = ensure(c->stage, sb);
+        // same pipeline as the injected normals: chunks of whole rows, copy stream || transpose kernel
+        rc = stream_rows_from_host(c, p, S, n_time_steps + 1, [&](const double* st, void* S0p, int64_t np) {
+            return launch_transpose_in(dtype, st, S0p, p->ld, n_time_steps + 1, np, c->stream);
+        });
         if (rc) { amc_paths_free(p); return rc; }
-        cudaError_t e = cudaMemcpyAsync(c->stage.p, S, sb, cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess)
-            e = launch_transpose_in(dtype, (const double*)c->stage.p, p->S, p->ld, n_time_steps + 1, n_paths_local, c->stream);
-        if (e != cudaSuccess) { amc_paths_free(p); return fail(AMC_ERR_CUDA, "adopting host paths: %s", cudaGetErrorString(e)); }
     }
     rc = measured_maps(c, p);
     if (rc) { amc_paths_free(p); return rc; }

@@ -392,3 +392,25 @@ def test_repeated_sweeps_replay_a_graph_with_identical_results(amc):
         np.testing.assert_array_equal(b, batch[0])
     assert abs(batch[0][0] - prices[0]) <= 1e-12 * prices[0] and abs(batch[0][1] - other) <= 1e-12 * other
     dp.free()
+
+
+def test_host_arrays_are_streamed_in_chunks_with_identical_results(amc, monkeypatch):
+    """Host normals / adopted host matrices go through two staging halves in chunks (copy stream || kernel): many small
+    chunks must give bit-identical path matrices and prices to a single chunk."""
+    rng = np.random.default_rng(17)
+    P, n = 70_001, 20
+    Z = rng.standard_normal((P, n))
+    monkeypatch.delenv("AMC_STAGE_CHUNK_MB", raising=False)
+    one = amc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0)
+    A = np.asarray(one)
+    price = amc.lsm_price(one, 40.0, 0.06, 0.05, "Put", None, "American", "Power", 3).price
+    monkeypatch.setenv("AMC_STAGE_CHUNK_MB", "1")                     # 1 MB chunks: ~11 chunks for Z, ~12 for the matrix
+    many = amc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0)
+    np.testing.assert_array_equal(np.asarray(many), A)
+    assert amc.lsm_price(many, 40.0, 0.06, 0.05, "Put", None, "American", "Power", 3).price == price
+    adopted = amc.paths_from_host(A)
+    np.testing.assert_array_equal(np.asarray(adopted), A)
+    adopted32 = amc.paths_from_host(A, dtype="float32")
+    np.testing.assert_array_equal(np.asarray(adopted32), A.astype(np.float32).astype(np.float64))
+    for d in (one, many, adopted, adopted32):
+        d.free()
