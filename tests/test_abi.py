@@ -67,3 +67,24 @@ def test_shard_range_partitions_the_path_axis():
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
         sizes = [hi - lo for lo, hi in parts]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(libamc_path, tmp_path):
+    """examples/price_put.c is a plain-C host of include/amc.h: it must compile and link against libamc.so; run without
+    a CUDA device it must stop at amc_ctx_create with the library's message (no CPU path), with one it prices."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    exe = tmp_path / "price_put"
+    libdir = os.path.dirname(libamc_path)
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "price_put.c"),
+           "-L", libdir, "-l:libamc.so", "-lm", f"-Wl,-rpath,{libdir}", "-o", str(exe)]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    if r.returncode == 0:
+        assert "American put K=40" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
