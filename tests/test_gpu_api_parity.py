@@ -86,3 +86,25 @@ def test_main_prints_reference_lines(amc, capsys, golden):
     assert printed[0] == "European Put Option Price with Barrier at 70 (LSMC): 4.0108"          # ipynb:312-313
     assert printed[1] == "European Put Option Price with Barrier at 70 (QuantLib): 4.0316"
     assert printed[2] == "European Put Option Price without Barrier (QuantLib): 9.8928"
+
+
+def test_plain_c_host_prices_through_the_abi(libamc_path, tmp_path):
+    """examples/price_put.c: a C program with no Python in the loop -- context, Philox paths, one contract, a batch."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(libamc_path)
+    exe = tmp_path / "price_put"
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "price_put.c"), "-L", libdir,
+                    "-l:libamc.so", "-lm", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    price = float(lines[0].split(":")[1].split()[0])
+    assert abs(price - 4.472) < 0.03                                   # Longstaff-Schwartz Table 1
+    ladder = [float(l.split()[1]) for l in lines[1:6]]
+    assert len(ladder) == 5 and all(b > a for a, b in zip(ladder, ladder[1:]))     # put price increases with the strike
+    assert abs(ladder[2] - price) <= 1e-9 * price                      # K = 40 inside the batch == the single contract
