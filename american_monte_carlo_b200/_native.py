@@ -25,7 +25,7 @@ class LsmSpec(C.Structure):
 
 class LsmSteps(C.Structure):
     _fields_ = [("gamma", c_double_p), ("beta", c_double_p), ("sv", c_double_p), ("mean_x", c_double_p),
-                ("std_x", c_double_p), ("rank", c_int_p)]
+                ("std_x", c_double_p), ("rank", c_int_p), ("pivot_loss", c_double_p)]
 
 
 class LsmTiming(C.Structure):

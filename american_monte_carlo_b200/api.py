@@ -23,6 +23,8 @@ import numpy as np
 from . import _native as N
 
 _BASES = ("Power", "Chebyshev", "Legendre")          # amc.py:99-101
+# conditioning report of the solve (include/amc.h: amc_lsm_steps.pivot_loss): parity with lstsq is tested up to here
+PIVOT_LOSS_WARN = 1e12
 _EXTRA_BASES = ("Laguerre",)                         # addition, BASELINE.json config 5
 
 
@@ -264,6 +266,7 @@ class LsmResult:
         self.n_time_steps, self.degree = n_time_steps, degree
         self.gamma, self.beta, self.sv = steps["gamma"], steps["beta"], steps["sv"]
         self.mean_x, self.std_x, self.rank = steps["mean_x"], steps["std_x"], steps["rank"]
+        self.pivot_loss = steps["pivot_loss"]
         self.timing = timing
         self.exercise_steps, self.cashflow0 = exercise_steps, cashflow0
 
@@ -304,10 +307,11 @@ def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="E
         rows = n + 1
         st = dict(gamma=np.zeros((rows, N.AMC_MAX_K)), beta=np.zeros((rows, N.AMC_MAX_K)),
                   sv=np.zeros((rows, N.AMC_MAX_K)), mean_x=np.zeros(rows), std_x=np.zeros(rows),
-                  rank=np.zeros(rows, dtype=np.int32))
+                  rank=np.zeros(rows, dtype=np.int32), pivot_loss=np.zeros(rows))
         steps = N.LsmSteps(gamma=st["gamma"].ctypes.data_as(N.c_double_p), beta=st["beta"].ctypes.data_as(N.c_double_p),
                            sv=st["sv"].ctypes.data_as(N.c_double_p), mean_x=st["mean_x"].ctypes.data_as(N.c_double_p),
-                           std_x=st["std_x"].ctypes.data_as(N.c_double_p), rank=st["rank"].ctypes.data_as(N.c_int_p))
+                           std_x=st["std_x"].ctypes.data_as(N.c_double_p), rank=st["rank"].ctypes.data_as(N.c_int_p),
+                           pivot_loss=st["pivot_loss"].ctypes.data_as(N.c_double_p))
         timing = N.LsmTiming()
         price = C.c_double()
         ex = np.empty(dp.n_paths_local, dtype=np.int32) if want_exercise_steps else None
@@ -318,7 +322,15 @@ def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="E
         tm = dict(total_ms=timing.total_ms, step_kernel_ms=timing.step_kernel_ms, solve_kernel_ms=timing.solve_kernel_ms,
                   step_launches=timing.step_launches, solve_launches=timing.solve_launches,
                   other_launches=timing.other_launches)
-        return LsmResult(np.float64(price.value), n, int(degree), st, tm, ex, cf)
+        res = LsmResult(np.float64(price.value), n, int(degree), st, tm, ex, cf)
+        worst = float(st["pivot_loss"].max()) if rows else 0.0
+        if worst > PIVOT_LOSS_WARN:
+            import warnings
+            t_bad = int(st["pivot_loss"].argmax())
+            warnings.warn(f"regression at step {t_bad}: the moment-based solve lost {math.log10(worst):.0f} digits "
+                          f"factorising the degree-{int(degree)} Gram of a very heavy-tailed column; rank decision and "
+                          "fit may deviate from numpy.linalg.lstsq -- lower the degree", RuntimeWarning, stacklevel=3)
+        return res
     finally:
         if temporary:
             dp.free()
@@ -563,7 +575,8 @@ def perform_backward_iteration(paths, cashflows, exercise_times, continuation_va
                          want_exercise_steps=1, want_svd=0, state_f32=0)
         rows = n + 1
         gamma = np.zeros((rows, N.AMC_MAX_K))
-        steps = N.LsmSteps(gamma=gamma.ctypes.data_as(N.c_double_p), beta=None, sv=None, mean_x=None, std_x=None, rank=None)
+        steps = N.LsmSteps(gamma=gamma.ctypes.data_as(N.c_double_p), beta=None, sv=None, mean_x=None, std_x=None, rank=None,
+                           pivot_loss=None)
         price = C.c_double()
         tau32 = np.empty(P, dtype=np.int32)
         N.check(N.lib().amc_lsm_price_with_hits(ctx.handle, dp.handle, C.byref(spec), first.ctypes.data, C.byref(price),

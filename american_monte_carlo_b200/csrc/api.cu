@@ -725,7 +725,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     const size_t nrow = (size_t)(n + 1);
     const size_t off_gamma = 0, off_beta = (size_t)C * nrow * kMaxK, off_sv = off_beta + nrow * kMaxK;
     const size_t off_ms = off_sv + nrow * kMaxK;
-    const size_t off_price = off_ms + 2 * nrow, off_rank = off_price + (size_t)C + 1;   // rank: int32 after the doubles
+    const size_t off_price = off_ms + 3 * nrow, off_rank = off_price + (size_t)C + 1;   // rank: int32 after the doubles
     const size_t diag_bytes = off_rank * 8 + nrow * 4;
     if ((rc = ensure(c->diag, diag_bytes))) return rc;
     double* dg = (double*)c->diag.p;
@@ -865,7 +865,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         s.gamma = dg + off_gamma + row * kMaxK;
         s.beta = dg + off_beta + row * kMaxK;
         s.sv = dg + off_sv + row * kMaxK;
-        s.mean_std = dg + off_ms + row * 2;
+        s.mean_std = dg + off_ms + row * 3;
         s.rank = drank + row;
         s.price = dg + off_price;
         s.n_batch = C;
@@ -991,8 +991,9 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         if (steps->beta) memcpy(steps->beta, diag_h.data() + off_beta, nrow * kMaxK * 8);
         if (steps->sv) memcpy(steps->sv, diag_h.data() + off_sv, nrow * kMaxK * 8);
         for (size_t t = 0; t < nrow; ++t) {
-            if (steps->mean_x) steps->mean_x[t] = diag_h[off_ms + 2 * t];
-            if (steps->std_x) steps->std_x[t] = diag_h[off_ms + 2 * t + 1];
+            if (steps->mean_x) steps->mean_x[t] = diag_h[off_ms + 3 * t];
+            if (steps->std_x) steps->std_x[t] = diag_h[off_ms + 3 * t + 1];
+            if (steps->pivot_loss) steps->pivot_loss[t] = diag_h[off_ms + 3 * t + 2];
             if (steps->rank) steps->rank[t] = rank_h[t];
         }
     }
@@ -1300,7 +1301,7 @@ static int regression_fit_impl(amc_ctx* c, const double* X, const double* Y, Pre
     s.beta = dg + kMaxK;
     s.sv = dg + 2 * kMaxK;
     s.mean_std = dg + 3 * kMaxK;
-    s.rank = (int*)(dg + 3 * kMaxK + 2);
+    s.rank = (int*)(dg + 3 * kMaxK + 3);
     s.price = dg + 3 * kMaxK + 4;
     e = launch_solve(s, c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "solve kernel: %s", cudaGetErrorString(e)));
@@ -1313,7 +1314,7 @@ static int regression_fit_impl(amc_ctx* c, const double* X, const double* Y, Pre
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "regression fit: %s", cudaGetErrorString(e)));
     if (beta) memcpy(beta, small + kMaxK, (size_t)(degree + 1) * 8);
-    if (rank) memcpy(rank, small + 3 * kMaxK + 2, 4);
+    if (rank) memcpy(rank, small + 3 * kMaxK + 3, 4);
     return cleanup(AMC_OK);
 }
 

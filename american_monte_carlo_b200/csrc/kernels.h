@@ -82,7 +82,7 @@ struct SolveArgs {
     double* gamma;             // [kMaxK]
     double* beta;              // [kMaxK]
     double* sv;                // [kMaxK]
-    double* mean_std;          // [2]
+    double* mean_std;          // [3]: mean, std of the column, pivot loss of the Gram factorisation
     int* rank;                 // [1]
     double* price;             // [1] (final_price)
     // batch: block c = blockIdx.x handles contract c: partials + c*n_rows rows, sums + c*kAccStride,

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
         if (a.beta) a.beta[i] = res.beta[i];
         if (a.sv) a.sv[i] = res.sv[i];
     }
-    if (a.mean_std) { a.mean_std[0] = res.mean_x; a.mean_std[1] = res.std_x; }
+    if (a.mean_std) { a.mean_std[0] = res.mean_x; a.mean_std[1] = res.std_x; a.mean_std[2] = res.pivot_loss; }
     if (a.rank) a.rank[0] = res.rank;
 }
 

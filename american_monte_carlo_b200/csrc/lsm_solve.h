@@ -58,6 +58,10 @@ struct SolveResult {
     double beta[kMaxK];       // numpy's lstsq coefficients in the USER basis (min-norm when truncated)
     double sv[kMaxK];         // singular values of the design matrix A, descending (only when the SVD ran)
     double mean_x, std_x;     // sample mean / population std of the column (np.mean, np.std)
+    double pivot_loss;        // max over accepted Cholesky pivots of G_jj / pivot_j (>= 1): how many digits the
+                              // factorisation of the internal Gram lost; ~cond(G).  Beyond ~1e12 the singular
+                              // values it yields are no longer accurate to numpy's cutoff eps*max(P,k) and the rank
+                              // decision (hence the fit) may deviate from lstsq -- reported, never hidden
     int rank;                 // numpy's reported rank
     int k_internal;           // internal monomials kept (== k unless the column is degenerate)
     int sweeps;               // Jacobi sweeps used; -1 = SVD skipped (full rank certified)
@@ -189,6 +193,7 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
     AMC_UNROLL
     for (int i = 0; i < kMaxK; ++i) out->gamma[i] = out->beta[i] = out->sv[i] = 0.0;
     out->sweeps = 0;
+    out->pivot_loss = 1.0;
 
     double Hn[2 * D + 1];
     AMC_UNROLL
@@ -232,6 +237,8 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
             } else {
                 const double ljj = sqrt(djj);
                 const double inv = 1.0 / ljj;
+                const double loss = Hn[2 * j] / djj;
+                if (loss > out->pivot_loss) out->pivot_loss = loss;
                 L[j][j] = ljj;
                 Linv[j] = inv;
                 AMC_UNROLL

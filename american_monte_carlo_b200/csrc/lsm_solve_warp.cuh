@@ -46,6 +46,7 @@ __device__ bool lsm_solve_warp(const SolveSpec& spec, const double* hsum /* [2d]
     for (int i = lane; i < K * (K + 1); i += 32) (&sh.L[0][0])[i] = 0.0;
     __syncwarp();
     const double pivot_tol = 2e-14;
+    double pivot_loss = 1.0;
     for (int j = 0; j < K; ++j) {
         double inv = 0.0;
         int ok = 1;
@@ -57,6 +58,7 @@ __device__ bool lsm_solve_warp(const SolveSpec& spec, const double* hsum /* [2d]
             } else {
                 const double ljj = sqrt(djj);
                 inv = 1.0 / ljj;
+                pivot_loss = sh.Hn[2 * j] / djj;
                 sh.L[j][j] = ljj;
                 sh.Linv[j] = inv;
             }
@@ -184,8 +186,10 @@ __device__ bool lsm_solve_warp(const SolveSpec& spec, const double* hsum /* [2d]
         if (beta_out) beta_out[lane] = lane < K ? sh.beta[lane] : 0.0;
         if (sv_out) sv_out[lane] = 0.0;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pivot_loss = fmax(pivot_loss, __shfl_xor_sync(FULL, pivot_loss, o));
     if (lane == 0) {
-        if (mean_std_out) { mean_std_out[0] = mean_x; mean_std_out[1] = std_x; }
+        if (mean_std_out) { mean_std_out[0] = mean_x; mean_std_out[1] = std_x; mean_std_out[2] = pivot_loss; }
         if (rank_out) rank_out[0] = K;
     }
     return true;

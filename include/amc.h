@@ -133,6 +133,11 @@ typedef struct amc_lsm_steps {
     double* mean_x;  /* [(n+1)] np.mean(paths[:, t]) */
     double* std_x;   /* [(n+1)] np.std(paths[:, t]) */
     int* rank;       /* [(n+1)] numpy's rank */
+    double* pivot_loss; /* [(n+1)] conditioning report of the moment-based solve: max over the Cholesky pivots of the
+                        internal Gram of G_jj / pivot_j (>= 1, ~cond(G); 0 where no regression ran).  Up to ~1e11 the
+                        rank decision and the fit reproduce numpy.linalg.lstsq (tests/, scripts/explore_rank.py); from
+                        ~1e12 on -- degree 10 on very heavy-tailed columns, sigma*sqrt(T) ~ 1 -- they may deviate:
+                        lower the degree (the Python host warns) */
 } amc_lsm_steps;     /* any pointer may be NULL */
 
 typedef struct amc_lsm_timing {

@@ -45,3 +45,26 @@ def test_random_small_contracts_match_the_oracle(c):
     flips = int((got.exercise_steps != want.exercise_times).sum())
     assert flips == 0, (c, flips)
     assert abs(got.price - want.price) <= 1e-10 * max(abs(want.price), 1e-6), (c, got.price, want.price)
+
+
+def test_conditioning_report_flags_what_the_moment_based_solve_cannot_reproduce(amc):
+    """Degree 10 on a very heavy-tailed column (sigma sqrt(T) = 0.9: standardised abscissae up to ~20, cond of the internal
+    Gram ~1e25) is beyond any Gram-based solve in double precision: numpy truncates to rank 5-6 there, the device solve
+    cannot resolve those singular values.  It must SAY so (pivot_loss, RuntimeWarning) instead of silently returning a
+    different price; the ordinary configurations must not warn.  (scripts/explore_rank.py: 300 random degree-4..10
+    contracts, 296 identical to the oracle in every decision; the 3 that deviate through the rank all report
+    pivot_loss > 5e12, every matching one < 2e11.)"""
+    import warnings
+    np.random.seed(122)
+    Z = orc.draw_normals(1169, 6)
+    dp = amc.paths_from_normals(Z, 250.0, 0.008157456534169638, 0.5208073312519027, 3.0)
+    with pytest.warns(RuntimeWarning, match="lower the degree"):
+        res = amc.lsm_price(dp, 240.7289820792065, 0.008157456534169638, 0.5, "Put", None, "American", "Legendre", 10,
+                            scaling=True, scaling_factor=1.0)
+    assert res.pivot_loss.max() > 1e12
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ok = amc.lsm_price(dp, 240.7289820792065, 0.008157456534169638, 0.5, "Put", None, "American", "Legendre", 4,
+                           scaling=True, scaling_factor=1.0)
+    assert 1.0 <= ok.pivot_loss[1:6].max() < 1e12 and ok.pivot_loss[6] == 0.0
+    dp.free()
