@@ -68,3 +68,23 @@ def test_conditioning_report_flags_what_the_moment_based_solve_cannot_reproduce(
                            scaling=True, scaling_factor=1.0)
     assert 1.0 <= ok.pivot_loss[1:6].max() < 1e12 and ok.pivot_loss[6] == 0.0
     dp.free()
+
+
+@pytest.mark.parametrize("basis,degree,kw", [("Power", 3, {}), ("Legendre", 5, dict(scaling=True)), ("Chebyshev", 8, dict(scaling=True))])
+def test_float_path_storage_is_exact_on_its_own_inputs(amc, basis, degree, kw):
+    """FP32 path storage changes the INPUTS (paths rounded to float), not the arithmetic: on the float-rounded paths
+    themselves the oracle (in double) and the device sweep must take identical decisions and agree to 1e-10; a float
+    state on top moves the price by its rounding only."""
+    n, P = 30, 120_001
+    dp = amc.generate_asset_paths(36.0, 0.06, 0.25, 1.0, n, P, rng="philox", seed=77, dtype="float32")
+    host = np.asarray(dp)                                    # the stored float values, exactly, as float64
+    assert np.array_equal(host, host.astype(np.float32).astype(np.float64))
+    want = orc.lsm_backward(host, 40.0, 0.06, 1.0 / n, "Put", None, "American", basis, degree, keep_continuation=False, **kw)
+    got = amc.lsm_price(dp, 40.0, 0.06, 1.0 / n, "Put", None, "American", basis, degree, want_exercise_steps=True, **kw)
+    assert int((got.exercise_steps != want.exercise_times).sum()) == 0
+    assert abs(got.price - want.price) <= 1e-10 * want.price
+    f32 = amc.lsm_price(dp, 40.0, 0.06, 1.0 / n, "Put", None, "American", basis, degree, want_exercise_steps=True,
+                        state_dtype="float32", **kw)
+    assert abs(f32.price - want.price) <= 2e-7 * want.price
+    assert (f32.exercise_steps != want.exercise_times).mean() < 1e-4
+    dp.free()
