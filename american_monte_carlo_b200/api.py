@@ -504,9 +504,11 @@ def regression_estimate(X, Y, basis_type="Power", degree=3, scaling=False, scali
     return out
 
 
-def apply_exercise(cashflows, exercise_times, exercise_value, continuation_estimated, t, indices):
-    """amc.py:90-94: where exercise_value > continuation_estimated (strict) set cashflows / exercise_times at `indices`.
-    Mutates `cashflows` (float64) and `exercise_times` (int64) in place, as the reference does."""
+def apply_exercise(cashflows, exercise_times, in_the_money_idx, exercise_value, continuation_estimated, t):
+    """amc.py:90-94 (same positional order): where exercise_value > continuation_estimated (strict) set cashflows /
+    exercise_times at `in_the_money_idx`.  Mutates `cashflows` (float64) and `exercise_times` (int64) in place, as the
+    reference does."""
+    indices = in_the_money_idx
     if not (isinstance(cashflows, np.ndarray) and cashflows.dtype == np.float64 and cashflows.flags.c_contiguous and
             isinstance(exercise_times, np.ndarray) and exercise_times.dtype == np.int64 and exercise_times.flags.c_contiguous):
         raise TypeError("cashflows must be a contiguous float64 ndarray and exercise_times a contiguous int64 ndarray "
@@ -542,9 +544,9 @@ def estimate_continuation_values(paths, t, r, dt, cashflows, exercise_times, bas
     return out
 
 
-def perform_backward_iteration(paths, cashflows, exercise_times, continuation_values, barrier_hit, K, r, dt, option_type,
-                               exercise_type, basis_type, degree, **kwargs):
-    """amc.py:139-167 with the reference's in-place contract: fills `cashflows` (undiscounted, float64) and
+def perform_backward_iteration(K, r, dt, n_time_steps, barrier_hit, cashflows, paths, option_type, exercise_times,
+                               exercise_type, continuation_values, basis_type, degree, **kwargs):
+    """amc.py:139-167 with the reference's positional order and in-place contract: fills `cashflows` (undiscounted, float64) and
     `exercise_times` (int64), appends one (t, paths[:, t], continuation_t) tuple per step to `continuation_values` and
     reverses that list (amc.py:164,167).  The whole loop runs as one device sweep.
 
@@ -560,6 +562,8 @@ def perform_backward_iteration(paths, cashflows, exercise_times, continuation_va
     dp, temporary = _as_device_paths(paths, ctx)
     try:
         n, P = dp.n_time_steps, dp.n_paths_local
+        if int(n_time_steps) != n:
+            raise ValueError(f"n_time_steps={n_time_steps} but paths has {n + 1} columns")
         hit = np.asarray(barrier_hit, dtype=bool)
         if hit.shape != (P, n + 1):
             raise ValueError(f"barrier_hit must have shape {(P, n + 1)}, got {hit.shape}")

@@ -712,7 +712,10 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         if (grid < 1) grid = 1;
     }
     const double rdt = spec->r * spec->dt;
-    const bool exchange = c->world > 1 && C == 1;     // batches are sharded by contract: no data-path collective
+    // the per-step exchange exists only where the path axis is really sharded over the ranks: a rank-local path set
+    // (n_global == n_local, e.g. an ndarray adopted under a multi-rank context) is priced by this rank alone, and
+    // batches are sharded by contract -- neither has a data-path collective
+    const bool exchange = c->world > 1 && C == 1 && p->n_global != p->n_local;
 
     // scratch
     const int64_t ldp = padded_len(P > 0 ? P : 1);

@@ -234,6 +234,13 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
             for (int c = 0; c < j; ++c) djj -= L[j][c] * L[j][c];
             if (!(djj > pivot_tol * Hn[2 * j])) {
                 kint = j;
+                // A rejected pivot beyond the constant-column case (j >= 2) with more paths than monomials is not an
+                // exactly degenerate column: the fit is truncated to the first j monomials WITHOUT numpy's singular-
+                // value rule having been applied to A, so the loss is reported (the host warns from 1e12 on).
+                if (j >= 2 && P > (double)K) {
+                    const double loss = (djj > 0.0) ? Hn[2 * j] / djj : 1e300;
+                    if (loss > out->pivot_loss) out->pivot_loss = loss;
+                }
             } else {
                 const double ljj = sqrt(djj);
                 const double inv = 1.0 / ljj;

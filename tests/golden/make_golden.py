@@ -13,6 +13,11 @@ Run:  python tests/golden/make_golden.py [--with-c2]
 
 `--with-c2` adds BASELINE.json configs[1] (10M paths x 50 steps, ~4 min, ~30 GB RSS).  Without
 the flag an existing c2 entry in golden.json is carried over unchanged.
+`--with-big` adds the reduced shapes of configs[2] and configs[4] that SURVEY.md section 8(c) pins
+(`c3_reduced` 1M x 252 Power-3 -> 4.4847469992..., `c5_reduced` 500k x 100 Legendre-8 scaled ->
+4.4890595342...; ~10 min, ~25 GB RSS) and writes every path's exercise step of those two runs to
+tests/golden/big_exercise_steps.npz (uint8, compressed) so that the GPU tier can count flipped
+decisions exactly without re-running a minute-long CPU sweep.  Carried over like c2 otherwise.
 /root/reference does not exist on the GPU box; nothing under tests/ reads it at test time.
 """
 import argparse
@@ -95,6 +100,16 @@ C2 = case("c2_power3_10M", LS, 50, 10_000_000, "Put", "American", None, "Power",
           source="BASELINE.json configs[1]")
 
 
+BIG = [
+    case("c3_reduced", LS, 252, 1_000_000, "Put", "American", None, "Power", 3, steps_detail=True,
+         source="BASELINE.json configs[2] at 1M paths (SURVEY.md 8c: 4.4847469992)"),
+    case("c5_reduced", LS, 100, 500_000, "Put", "American", None, "Legendre", 8,
+         dict(scaling=True, scaling_factor=2), steps_detail=True,
+         source="BASELINE.json configs[4] at 500k paths, the reference-comparable basis (SURVEY.md 8c: 4.4890595342)"),
+]
+BIG_EXPECT = {"c3_reduced": "4.4847469992", "c5_reduced": "4.4890595342"}
+
+
 class LstsqTap:
     """Wrap np.linalg.lstsq to record what numpy itself reports for each call."""
 
@@ -115,7 +130,7 @@ class LstsqTap:
         np.linalg.lstsq = self._orig
 
 
-def run_case(c, check_oracle=True):
+def run_case(c, check_oracle=True, keep_tau=None):
     t0 = time.time()
     mk = (c["S0"], c["r"], c["sigma"], c["T"], c["n_time_steps"], c["n_paths"])
     dt = c["T"] / c["n_time_steps"]
@@ -165,6 +180,11 @@ def run_case(c, check_oracle=True):
         rec["cont_probe"] = {str(t): [float(v) for v in cont[t][2][:8]] for t in pick}
         rec["cont_mean"] = {str(t): float(np.mean(cont[t][2])) for t in pick}
     rec["seconds"] = round(time.time() - t0, 2)
+    if keep_tau is not None:
+        assert n < 256
+        keep_tau[c["name"]] = tau.astype(np.uint8)
+    if c["name"] in BIG_EXPECT:
+        assert f"{price:.10f}" == BIG_EXPECT[c["name"]], (c["name"], price)
     if c["name"] in NB_PRINTED:
         assert f"{price:.4f}" == NB_PRINTED[c["name"]], (c["name"], price)
         rec["printed_in_notebook"] = NB_PRINTED[c["name"]]
@@ -176,16 +196,29 @@ def run_case(c, check_oracle=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--with-c2", action="store_true")
+    ap.add_argument("--with-big", action="store_true")
+    ap.add_argument("--only-big", action="store_true", help="carry every other case over from the existing file")
     args = ap.parse_args()
     out_path = os.path.join(HERE, "golden.json")
     old = {}
     if os.path.exists(out_path):
         old = {r["name"]: r for r in json.load(open(out_path))["cases"]}
-    recs = [run_case(c) for c in CASES]
+    if args.only_big:
+        recs = [old[c["name"]] for c in CASES]
+        args.with_big = True
+    else:
+        recs = [run_case(c) for c in CASES]
     if args.with_c2:
         recs.append(run_case(C2))
     elif C2["name"] in old:
         recs.append(old[C2["name"]])
+    if args.with_big:
+        taus = {}
+        for c in BIG:
+            recs.append(run_case(c, keep_tau=taus))
+        np.savez_compressed(os.path.join(HERE, "big_exercise_steps.npz"), **taus)
+    else:
+        recs += [old[c["name"]] for c in BIG if c["name"] in old]
     meta = dict(numpy=np.__version__, generator="tests/golden/make_golden.py",
                 reference="/root/reference/american_monte_carlo.py (unmodified; matplotlib/QuantLib stubbed)",
                 note="oracle/lsm_oracle.py was asserted bit-identical to the reference on every case")

@@ -91,6 +91,17 @@ def main():
     rh = amc.lsm_price(dh, K, r, T / n, "Put", None, "American", "Power", 3, ctx=ctx)
     out["adopted"] = dict(price=float(rh.price), mu_err=float(np.max(np.abs(mu - paths.mean(axis=0)) / mu)),
                           sg_err=float(np.max(np.abs(sg[1:] - paths.std(axis=0)[1:]) / sg[1:])))
+    # (4) a host ndarray handed to the reference-shaped entry point under a multi-rank default context is a rank-LOCAL
+    # path set (n_global == n_local): no exchange, every rank prices all of it by itself and gets the oracle's price
+    small = np.ascontiguousarray(paths[:20_000])
+    want_small = orc.lsm_backward(small, K, r, T / n, "Put", None, "American", "Power", 3, keep_continuation=False)
+    got_small, _ = amc.lsmc_option_pricing(small, K, r, T / n, "Put", None, "American", "Power", 3)
+    if rank == 1:        # only one rank calls a second time: a stray exchange would wait for the others and time out
+        again, _ = amc.lsmc_option_pricing(small, K, r, T / n, "Put", None, "American", "Power", 3)
+        assert again == got_small
+    errs = torch.tensor([abs(float(got_small) - float(want_small.price)) / float(want_small.price)], device="cuda")
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    out["local_ndarray"] = dict(max_rel_err=float(errs.item()))
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out))
     dist.barrier()

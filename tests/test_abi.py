@@ -88,3 +88,43 @@ def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(liba
         assert "American put K=40" in r.stdout
     else:
         assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
+
+
+# the reference's positional parameter order (american_monte_carlo.py:72,85,90,98,110,126,139-140,171,180-182); a
+# reference-style positional call must bind the same way through the shim
+REFERENCE_SIGNATURES = {
+    "generate_asset_paths": ["S0", "r", "sigma", "T", "n_time_steps", "n_paths"],
+    "intrinsic_value": ["S", "K", "option_type"],
+    "apply_exercise": ["cashflows", "exercise_times", "in_the_money_idx", "exercise_value", "continuation_estimated", "t"],
+    "get_basis_polynomials": ["X", "basis_type", "degree"],
+    "regression_estimate": ["X", "Y", "basis_type", "degree", "scaling", "scaling_factor"],
+    "estimate_continuation_values": ["paths", "t", "r", "dt", "cashflows", "exercise_times", "basis_type", "degree"],
+    "perform_backward_iteration": ["K", "r", "dt", "n_time_steps", "barrier_hit", "cashflows", "paths", "option_type",
+                                   "exercise_times", "exercise_type", "continuation_values", "basis_type", "degree"],
+    "precompute_barrier_hit_matrix": ["paths", "barrier_level"],
+    "lsmc_option_pricing": ["paths", "K", "r", "dt", "option_type", "barrier_level", "exercise_type", "basis_type", "degree"],
+    "compute_ccr_exposures": ["continuation_values"],
+}
+
+
+def _positional(fn):
+    import inspect
+    return [p.name for p in inspect.signature(fn).parameters.values()
+            if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+
+
+def test_shim_keeps_the_reference_positional_order():
+    import american_monte_carlo as shim
+    for name, want in REFERENCE_SIGNATURES.items():
+        assert _positional(getattr(shim, name)) == want, name
+
+
+def test_signature_table_matches_the_reference_when_it_is_present():
+    ref_py = "/root/reference/american_monte_carlo.py"
+    if not os.path.exists(ref_py):
+        pytest.skip("reference checkout not present (GPU box)")
+    import ast
+    tree = ast.parse(open(ref_py).read())
+    defs = {n.name: [a.arg for a in n.args.args] for n in tree.body if isinstance(n, ast.FunctionDef)}
+    for name, want in REFERENCE_SIGNATURES.items():
+        assert defs[name] == want, name

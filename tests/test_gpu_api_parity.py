@@ -19,12 +19,12 @@ def test_apply_exercise_in_place(amc):
     mask = ev > ce
     want_cf[idx[mask]] = ev[mask]
     want_tau[idx[mask]] = 7
-    amc.apply_exercise(cf, tau, ev, ce, 7, idx)
+    amc.apply_exercise(cf, tau, idx, ev, ce, 7)
     np.testing.assert_array_equal(cf, want_cf)
     np.testing.assert_array_equal(tau, want_tau)
     with pytest.raises(IndexError):
-        amc.apply_exercise(cf, tau, ev[:1], ce[:1], 7, np.array([P]))
-    amc.apply_exercise(cf, tau, ev[:0], ce[:0], 7, idx[:0])       # empty candidate set (amc.py:158 guards it)
+        amc.apply_exercise(cf, tau, np.array([P]), ev[:1], ce[:1], 7)
+    amc.apply_exercise(cf, tau, idx[:0], ev[:0], ce[:0], 7)       # empty candidate set (amc.py:158 guards it)
 
 
 @pytest.mark.parametrize("basis,degree,kwargs", [("Power", 3, {}), ("Chebyshev", 4, dict(scaling=True, scaling_factor=1))])
@@ -52,7 +52,7 @@ def test_perform_backward_iteration_contract(amc, opt, ex, barrier):
     cashflows, exercise_times, cont = np.zeros(P), np.full(P, n), []
     hit = amc.precompute_barrier_hit_matrix(paths, barrier)
     np.testing.assert_array_equal(hit, orc.knock_in_flags(paths, barrier))
-    amc.perform_backward_iteration(paths, cashflows, exercise_times, cont, hit, 40.0, 0.06, 1.0 / n, opt, ex, "Power", 3)
+    amc.perform_backward_iteration(40.0, 0.06, 1.0 / n, n, hit, cashflows, paths, opt, exercise_times, ex, cont, "Power", 3)
     np.testing.assert_array_equal(exercise_times, want.exercise_times)
     np.testing.assert_array_equal(cashflows, want.cashflows)              # payoff at the exercise step: exact
     price = np.mean(cashflows * np.exp(-0.06 * (1.0 / n) * exercise_times))   # amc.py:196
@@ -65,7 +65,7 @@ def test_perform_backward_iteration_contract(amc, opt, ex, barrier):
     bad[0, :] = False
     bad[0, 3] = True                                                       # not a running OR
     with pytest.raises(NotImplementedError):
-        amc.perform_backward_iteration(paths, cashflows, exercise_times, [], bad, 40.0, 0.06, 1.0 / n, opt, ex, "Power", 3)
+        amc.perform_backward_iteration(40.0, 0.06, 1.0 / n, n, bad, cashflows, paths, opt, exercise_times, ex, [], "Power", 3)
 
 
 def test_main_prints_reference_lines(amc, capsys, golden):

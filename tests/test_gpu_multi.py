@@ -45,3 +45,4 @@ def test_sharded_sweep_equals_single_gpu_and_oracle(libamc_path, allreduce):
     ad = out["adopted"]
     assert abs(ad["price"] - inj["oracle"]) <= 1e-10 * inj["oracle"]
     assert ad["mu_err"] < 1e-12 and ad["sg_err"] < 1e-10
+    assert out["local_ndarray"]["max_rel_err"] <= 1e-10          # rank-local path set: no exchange

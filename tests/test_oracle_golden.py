@@ -23,6 +23,18 @@ def test_golden_has_reference_known_answers(golden):
     assert golden["c1_power3"]["price"] == 4.4783398987704475
     assert golden["c2_power3_10M"]["price"] == 4.475181386178888      # BASELINE.md, lstsq rank 3 at t=1
     assert golden["c2_power3_10M"]["ranks"][1] == 3
+    # the reduced shapes of configs[2] and configs[4], from the reference itself
+    assert f"{golden['c3_reduced']['price']:.10f}" == "4.4847469992"
+    assert f"{golden['c5_reduced']['price']:.10f}" == "4.4890595342"
+
+
+def test_big_exercise_step_fixture_matches_its_goldens(golden):
+    steps = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "big_exercise_steps.npz"))
+    for name in ("c3_reduced", "c5_reduced"):
+        c = golden[name]
+        tau = steps[name]
+        assert tau.shape == (c["n_paths"],) and tau.dtype == np.uint8
+        assert np.bincount(tau, minlength=c["n_time_steps"] + 1).tolist() == c["exercise_step_hist"]
 
 
 def test_oracle_reproduces_every_small_golden_case_bitwise(golden):
