@@ -48,6 +48,8 @@ PROTOTYPES = {
     "amc_comm_allreduce_host": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "amc_paths_generate": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int64,
                                      C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "amc_paths_generate_lean": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int64,
+                                          C.c_int64, C.c_int64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "amc_paths_from_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     "amc_paths_from_normals_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -79,6 +81,9 @@ PROTOTYPES = {
                                      C.c_int64, C.c_int64]),
     "amc_basis_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "amc_barrier_hit_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "amc_selftest_philox": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "amc_selftest_normals": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_double,
+                                       C.c_double, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

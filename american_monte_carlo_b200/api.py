@@ -189,15 +189,20 @@ class DevicePaths:
             pass
 
 
-def shard_range(n_paths_global: int, world_size: int, rank: int):
-    """Contiguous block partition of the path axis: rank g owns [lo, hi).  Sizes differ by at most one."""
-    base, rem = divmod(int(n_paths_global), int(world_size))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+def shard_range(n_paths_global: int, world_size: int, rank: int, unit: int = 1):
+    """Contiguous block partition of the path axis: rank g owns [lo, hi).  Sizes differ by at most `unit` paths; with
+    unit=4 every shard starts on a quad boundary (one Philox call of the float generator serves four adjacent paths:
+    aligned shards keep 128-bit stores and are what the path-free mode requires)."""
+    n, unit = int(n_paths_global), int(unit)
+    blocks = -(-n // unit)
+    base, rem = divmod(blocks, int(world_size))
+    lo_b = rank * base + min(rank, rem)
+    hi_b = lo_b + base + (1 if rank < rem else 0)
+    return min(lo_b * unit, n), min(hi_b * unit, n)
 
 
 def generate_asset_paths(S0, r, sigma, T, n_time_steps, n_paths, *, rng="numpy", dtype="float64", seed=None,
-                         ctx: Context | None = None):
+                         store_paths=True, ctx: Context | None = None):
     """amc.py:72-81 on the GPU.  `n_paths` is the GLOBAL path count; under a multi-rank context each rank
     simulates its own contiguous shard.
 
@@ -206,12 +211,23 @@ def generate_asset_paths(S0, r, sigma, T, n_time_steps, n_paths, *, rng="numpy",
                  paths -- and the GPU does exp / cumulative step / layout (kernel K1z).
     rng="philox" (throughput): counter-based Philox4x32-10 + Box-Muller on the device (kernel K1).  The 64-bit seed
                  is `seed`, or one draw from the global NumPy stream so np.random.seed(...) still makes runs repeatable.
+                 store_paths=False (float32 only) keeps NO path matrix: 4 bytes per path instead of 4 (n+1); the backward
+                 sweep regenerates the columns from the counters and takes the same decisions as the stored set.
     """
     ctx = ctx or default_context()
     n_time_steps, n_paths = int(n_time_steps), int(n_paths)
     did = _dtype_id(dtype)
-    lo, hi = shard_range(n_paths, ctx.world_size, ctx.rank)
+    lo, hi = shard_range(n_paths, ctx.world_size, ctx.rank, 4 if (rng == "philox" and did == N.F32) else 1)
     h = C.c_void_p()
+    if not store_paths:
+        if rng != "philox" or did != N.F32:
+            raise ValueError("store_paths=False needs rng='philox' and dtype='float32' (the columns are regenerated from "
+                             "the Philox counters of the float generator)")
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 62))
+        N.check(N.lib().amc_paths_generate_lean(ctx.handle, float(S0), float(r), float(sigma), float(T), n_time_steps,
+                                                hi - lo, lo, n_paths, C.c_uint64(int(seed)), C.byref(h)))
+        return DevicePaths(ctx, h, hi - lo, n_paths, n_time_steps, did, lo)
     if rng == "numpy":
         if ctx.world_size != 1:
             raise ValueError("rng='numpy' replays the reference's single global stream; use rng='philox' when sharded")

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -52,6 +53,8 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
 };
 static NcclApi g_nccl;
 
@@ -71,6 +74,8 @@ static int nccl_load() {
     SYM(AllReduce, "ncclAllReduce")
     SYM(AllGather, "ncclAllGather")
     SYM(GetErrorString, "ncclGetErrorString")
+    SYM(CommGetAsyncError, "ncclCommGetAsyncError")
+    SYM(CommAbort, "ncclCommAbort")
 #undef SYM
     g_nccl.handle = h;
     return AMC_OK;
@@ -104,7 +109,12 @@ struct amc_ctx {
     void* peer_mailbox[kPeerMax] = {};
     int* peer_err = nullptr;
     // grow-only scratch (one pricing call at a time per context)
-    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab, ccr;
+    DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab, ccr, tabs, syncbuf, lstate, regx;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;      // around the persistent sweep kernel
+    int sweep_grid_cache[4][AMC_MAX_K];
+    uint32_t peer_seq = 0;          // sequence numbers of the peer exchange are handed out per sweep by the host: every
+                                    // rank advances by the same amount per sharded sweep, also when a sweep failed
+    std::vector<amc_paths*> live_paths;   // path sets not yet freed: invalidated (not leaked, not dangling) on destroy
     std::vector<cudaEvent_t> events;
     int grid_cache[3][AMC_MAX_K];
     // freed path matrices are kept for reuse (all work is ordered on one stream, so a recycled buffer is safe):
@@ -121,8 +131,15 @@ struct amc_ctx {
 constexpr size_t kPathPoolMax = 2;
 
 struct amc_paths {
-    amc_ctx* ctx = nullptr;
-    void* S = nullptr;
+    amc_ctx* ctx = nullptr;         // null once the context has been destroyed (the handle can still be freed)
+    void* S = nullptr;              // null for a lean (path-free) set
+    // lean set: terminal fixed-point log2-prices + what regenerates every earlier column (gbm_quad.cuh)
+    bool lean = false, borrowed = false;
+    int32_t* Ln = nullptr;
+    QuadGen gen = {};
+    int rounds = 10;
+    int64_t path_offset = 0;
+    uint64_t seed = 0;
     int64_t ld = 0, n_local = 0, n_global = 0;
     int n_steps = 0, dtype = 0;
     size_t bytes = 0;
@@ -138,6 +155,45 @@ static int ensure(DevBuf& b, size_t bytes) {
     CU(cudaMalloc(&b.p, want));
     b.cap = want;
     return AMC_OK;
+}
+
+// Wait for the context stream while NCCL kernels may be in flight: a lost rank would otherwise leave the collective (and
+// this host thread) waiting forever.  The stream is polled; every pass asks the communicator for asynchronous errors, and
+// a wall-clock limit (AMC_NCCL_TIMEOUT_S, default 120) bounds the wait.  On either, the communicator is aborted -- which
+// releases the stuck kernels -- and the call fails with AMC_ERR_NCCL; the context has no communicator afterwards.
+static int sync_with_nccl_watchdog(amc_ctx* c) {
+    if (!c->comm || !g_nccl.CommGetAsyncError) {
+        CU(cudaStreamSynchronize(c->stream));
+        return AMC_OK;
+    }
+    static const double limit_s = getenv("AMC_NCCL_TIMEOUT_S") ? atof(getenv("AMC_NCCL_TIMEOUT_S")) : 120.0;
+    timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned spins = 0;; ++spins) {
+        cudaError_t q = cudaStreamQuery(c->stream);
+        if (q == cudaSuccess) return AMC_OK;
+        if (q != cudaErrorNotReady) return fail(AMC_ERR_CUDA, "stream: %s", cudaGetErrorString(q));
+        ncclResult_t async = ncclSuccess;
+        ncclResult_t r = g_nccl.CommGetAsyncError(c->comm, &async);
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double waited = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        const bool failed = (r != ncclSuccess) || (async != ncclSuccess && async != ncclInProgress);
+        if (failed || waited > limit_s) {
+            const char* why = failed ? g_nccl.GetErrorString(r != ncclSuccess ? r : async) : "no progress within the time limit";
+            g_nccl.CommAbort(c->comm);
+            c->comm = nullptr;
+            c->transport = 0;
+            c->world = 1;
+            cudaStreamSynchronize(c->stream);
+            return fail(AMC_ERR_NCCL, "NCCL all-reduce of the moment sums did not complete (%s, waited %.1f s): a rank is gone; "
+                                      "the communicator has been aborted", why, waited);
+        }
+        if (spins > 1000) {
+            timespec nap = {0, 200000};           // 0.2 ms between polls once the first millisecond has passed
+            nanosleep(&nap, nullptr);
+        }
+    }
 }
 
 static size_t elem_size(int dtype) { return dtype == AMC_F32 ? 4 : 8; }
@@ -170,6 +226,8 @@ extern "C" int amc_ctx_create(int device, void* stream, amc_ctx** out) {
     }
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < AMC_MAX_K; ++j) c->grid_cache[i][j] = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < AMC_MAX_K; ++j) c->sweep_grid_cache[i][j] = 0;
     *out = c;
     return AMC_OK;
 }
@@ -183,7 +241,19 @@ extern "C" int amc_ctx_destroy(amc_ctx* c) {
     if (c->mailbox) cudaFree(c->mailbox);
     if (c->peer_err) cudaFree(c->peer_err);
     if (c->comm && g_nccl.handle) g_nccl.CommDestroy(c->comm);
-    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc, &c->batch_tab, &c->ccr};
+    // path sets that outlive their context keep a valid handle: their device memory goes with the context
+    for (amc_paths* p : c->live_paths) {
+        if (p->S) cudaFree(p->S);
+        if (p->Ln) cudaFree(p->Ln);
+        p->S = nullptr;
+        p->Ln = nullptr;
+        p->ctx = nullptr;
+    }
+    c->live_paths.clear();
+    for (cudaEvent_t ev : {c->ev_k0, c->ev_k1})
+        if (ev) cudaEventDestroy(ev);
+    DevBuf* bufs[] = {&c->U, &c->tau, &c->first_hit, &c->partials, &c->sums, &c->diag, &c->stage, &c->misc, &c->batch_tab, &c->ccr,
+                      &c->tabs, &c->syncbuf, &c->lstate, &c->regx};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf& b : c->path_pool)
@@ -233,18 +303,30 @@ extern "C" int amc_comm_unique_id(char id[128]) {
 static int peer_setup(amc_ctx* c) {
     const int W = c->world;
     if (W > kPeerMax) return fail(AMC_ERR_NCCL, "peer-memory all-reduce supports up to %d ranks", kPeerMax);
+    // Every rank takes part in BOTH agreement collectives below whatever happens locally (a rank that left early would
+    // leave its peers blocked inside NCCL): local failures only clear `ok`.
     const size_t box_bytes = (size_t)kPeerRing * W * kAccStride * sizeof(uint4);
-    CU(cudaMalloc(&c->mailbox, box_bytes));
-    CU(cudaMalloc((void**)&c->peer_err, 256));
-    CU(cudaMemsetAsync(c->mailbox, 0, box_bytes, c->stream));
-    CU(cudaMemsetAsync(c->peer_err, 0, 256, c->stream));
-    CU(cudaStreamSynchronize(c->stream));              // zeroed before any peer can learn the handle
-    cudaIpcMemHandle_t mine;
     int ok = 1;
-    if (cudaIpcGetMemHandle(&mine, c->mailbox) != cudaSuccess) { ok = 0; memset(&mine, 0, sizeof(mine)); cudaGetLastError(); }
+    char why[200] = "";
+    auto note = [&](const char* what, cudaError_t e) {
+        if (e == cudaSuccess) return;
+        if (ok) snprintf(why, sizeof(why), "%s: %s", what, cudaGetErrorString(e));
+        ok = 0;
+        cudaGetLastError();
+    };
+    note("cudaMalloc(mailbox)", cudaMalloc(&c->mailbox, box_bytes));
+    note("cudaMalloc(flags)", cudaMalloc((void**)&c->peer_err, 256));
+    if (ok) {
+        note("memset", cudaMemsetAsync(c->mailbox, 0, box_bytes, c->stream));
+        note("memset", cudaMemsetAsync(c->peer_err, 0, 256, c->stream));
+        note("sync", cudaStreamSynchronize(c->stream));          // zeroed before any peer can learn the handle
+    }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) note("cudaIpcGetMemHandle", cudaIpcGetMemHandle(&mine, c->mailbox));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     int rc = ensure(c->misc, 64 * (size_t)(W + 1) + 64);
-    if (rc) return rc;
+    if (rc) return rc;                                          // nothing can be exchanged without this scratch
     char* send = (char*)c->misc.p;
     char* recv = send + 64;
     CU(cudaMemcpyAsync(send, &mine, 64, cudaMemcpyHostToDevice, c->stream));
@@ -252,15 +334,14 @@ static int peer_setup(amc_ctx* c) {
     std::vector<cudaIpcMemHandle_t> all(W);
     CU(cudaMemcpyAsync(all.data(), recv, 64 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    char why[160] = "";
     for (int q = 0; q < W && ok; ++q) {
         if (q == c->rank) { c->peer_mailbox[q] = c->mailbox; continue; }
         cudaError_t e = cudaIpcOpenMemHandle(&c->peer_mailbox[q], all[q], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
-            snprintf(why, sizeof(why), "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
             c->peer_mailbox[q] = nullptr;
-            cudaGetLastError();
-            ok = 0;
+            char what[64];
+            snprintf(what, sizeof(what), "cudaIpcOpenMemHandle(rank %d)", q);
+            note(what, e);
         }
     }
     // agreement: sum of ok flags must equal W
@@ -328,7 +409,12 @@ extern "C" int amc_comm_allreduce_host(amc_ctx* c, double* buf, int n) {
 
 // ---------------------------------------------------------------------------------------------------------
 // paths
-static int paths_alloc(amc_ctx* c, int n_steps, int64_t n_local, int64_t n_global, int dtype, amc_paths** out) {
+enum PathKind { kPathMatrix = 0, kPathLean = 1, kPathBorrowed = 2 };
+
+// kPathMatrix: the [n+1][ld] matrix (pooled); kPathLean: only the terminal log-price vector; kPathBorrowed: one column
+// living in the context's regression scratch (regx) -- never pooled, never freed with the handle
+static int paths_alloc(amc_ctx* c, int n_steps, int64_t n_local, int64_t n_global, int dtype, amc_paths** out,
+                       int kind = kPathMatrix) {
     if (!c || !out) return fail(AMC_ERR_VALUE, "null argument");
     if (n_steps < 0 || n_local < 0 || n_global < n_local)
         return fail(AMC_ERR_VALUE, "bad path-set shape: n_time_steps=%d n_paths_local=%lld n_paths_global=%lld", n_steps,
@@ -342,6 +428,38 @@ static int paths_alloc(amc_ctx* c, int n_steps, int64_t n_local, int64_t n_globa
     p->n_global = n_global;
     p->dtype = dtype;
     p->ld = padded_len(n_local > 0 ? n_local : 1);
+    p->mu.assign(n_steps + 1, 0.0);
+    p->sigma.assign(n_steps + 1, 1.0);
+    if (kind == kPathLean) {
+        p->lean = true;
+        p->bytes = (size_t)p->ld * 4;
+        for (size_t i = 0; i < c->path_pool.size(); ++i) {
+            if (c->path_pool[i].cap == p->bytes) {
+                p->Ln = (int32_t*)c->path_pool[i].p;
+                c->path_pool.erase(c->path_pool.begin() + i);
+                break;
+            }
+        }
+        if (!p->Ln) {
+            cudaError_t e = cudaMalloc((void**)&p->Ln, p->bytes);
+            if (e != cudaSuccess) {
+                delete p;
+                return fail(AMC_ERR_CUDA, "cudaMalloc of the log-price vector failed: %s", cudaGetErrorString(e));
+            }
+        }
+        c->live_paths.push_back(p);
+        *out = p;
+        return AMC_OK;
+    }
+    if (kind == kPathBorrowed) {
+        p->borrowed = true;
+        p->bytes = (size_t)p->ld * (size_t)(n_steps + 1) * elem_size(dtype);
+        int rc = ensure(c->regx, p->bytes);
+        if (rc) { delete p; return rc; }
+        p->S = c->regx.p;
+        *out = p;
+        return AMC_OK;
+    }
     p->bytes = (size_t)p->ld * (size_t)(n_steps + 1) * elem_size(dtype);
     for (size_t i = 0; i < c->path_pool.size(); ++i) {
         if (c->path_pool[i].cap == p->bytes) {
@@ -364,8 +482,7 @@ static int paths_alloc(amc_ctx* c, int n_steps, int64_t n_local, int64_t n_globa
             return fail(AMC_ERR_CUDA, "cudaMalloc of %zu bytes for the path matrix failed: %s", bytes, cudaGetErrorString(e));
         }
     }
-    p->mu.assign(n_steps + 1, 0.0);
-    p->sigma.assign(n_steps + 1, 1.0);
+    c->live_paths.push_back(p);
     *out = p;
     return AMC_OK;
 }
@@ -401,8 +518,38 @@ extern "C" int amc_paths_generate(amc_ctx* c, double S0, double r, double sigma,
     int rc = paths_alloc(c, n_time_steps, n_paths_local, n_paths_global, dtype, &p);
     if (rc) return rc;
     if (n_paths_local > 0) {
-        cudaError_t e = launch_generate_philox(dtype, p->S, p->ld, n_time_steps, n_paths_local, path_offset,
+        cudaError_t e = launch_generate_philox(dtype, p->S, nullptr, p->ld, n_time_steps, n_paths_local, path_offset,
                                                gbm_params(S0, r, sigma, T, n_time_steps), seed, c->sm_count, c->stream);
+        if (e != cudaSuccess) {
+            amc_paths_free(p);
+            return fail(AMC_ERR_CUDA, "philox path kernel launch: %s", cudaGetErrorString(e));
+        }
+    }
+    analytic_maps(p, S0, r, sigma, T);
+    *out = p;
+    return AMC_OK;
+}
+
+// Path-free ("lean") set: nothing but the terminal log2-prices is stored (4 bytes per path instead of 4 (n+1)); the
+// backward sweep regenerates every earlier column from the Philox counters (lsm_sweep.cuh, LEAN).  Float generator only.
+extern "C" int amc_paths_generate_lean(amc_ctx* c, double S0, double r, double sigma, double T, int n_time_steps,
+                                       int64_t n_paths_local, int64_t path_offset, int64_t n_paths_global, uint64_t seed,
+                                       amc_paths** out) {
+    if (n_time_steps < 1) return fail(AMC_ERR_VALUE, "n_time_steps must be >= 1");
+    if (path_offset & 3)
+        return fail(AMC_ERR_VALUE, "amc_paths_generate_lean: path_offset %lld is not a multiple of 4 (one Philox call "
+                                   "serves four adjacent paths; shard in units of 4 paths)", (long long)path_offset);
+    amc_paths* p = nullptr;
+    int rc = paths_alloc(c, n_time_steps, n_paths_local, n_paths_global, AMC_F32, &p, kPathLean);
+    if (rc) return rc;
+    const GbmParams g = gbm_params(S0, r, sigma, T, n_time_steps);
+    p->gen = make_quad_gen(g, n_time_steps, seed);
+    p->rounds = philox_rounds();
+    p->path_offset = path_offset;
+    p->seed = seed;
+    if (n_paths_local > 0) {
+        cudaError_t e = launch_generate_philox(AMC_F32, nullptr, p->Ln, p->ld, n_time_steps, n_paths_local, path_offset, g, seed,
+                                               c->sm_count, c->stream);
         if (e != cudaSuccess) {
             amc_paths_free(p);
             return fail(AMC_ERR_CUDA, "philox path kernel launch: %s", cudaGetErrorString(e));
@@ -582,7 +729,16 @@ extern "C" int amc_paths_from_host(amc_ctx* c, const double* S, int n_time_steps
 extern "C" int amc_paths_free(amc_paths* p) {
     if (!p) return AMC_OK;
     amc_ctx* c = p->ctx;
+    if (!c || p->borrowed) {            // the context is gone (its destroy released the device memory), or a scratch view
+        delete p;
+        return AMC_OK;
+    }
     cudaSetDevice(c->device);
+    for (size_t i = 0; i < c->live_paths.size(); ++i)
+        if (c->live_paths[i] == p) { c->live_paths.erase(c->live_paths.begin() + i); break; }
+    void* mem = p->S ? p->S : (void*)p->Ln;
+    p->Ln = nullptr;
+    p->S = mem;
     if (p->S) {
         if (c->path_pool.size() < kPathPoolMax) {
             DevBuf b;
@@ -614,8 +770,15 @@ extern "C" int amc_paths_column(const amc_paths* p, int t, double* out) {
     if (t < 0 || t > p->n_steps) return fail(AMC_ERR_VALUE, "column %d out of range 0..%d", t, p->n_steps);
     if (p->n_local == 0) return AMC_OK;
     amc_ctx* c = p->ctx;
+    if (!c) return fail(AMC_ERR_STATE, "the path set's context has been destroyed");
     CU(cudaSetDevice(c->device));
-    if (p->dtype == AMC_F64) {
+    if (p->lean) {
+        int rc = ensure(c->misc, (size_t)p->n_local * 8);
+        if (rc) return rc;
+        CU(launch_lean_walk(0, p->rounds, p->gen, p->path_offset >> 2, p->n_local, p->n_steps, t, 0, p->n_local, 0.0, nullptr,
+                            (double*)c->misc.p, nullptr, c->sm_count, c->stream));
+        CU(cudaMemcpyAsync(out, c->misc.p, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
+    } else if (p->dtype == AMC_F64) {
         CU(cudaMemcpyAsync(out, column(p, t), (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
     } else {
         int rc = ensure(c->misc, (size_t)p->n_local * 8);
@@ -633,11 +796,16 @@ extern "C" int amc_paths_rows(const amc_paths* p, int64_t p0, int64_t p1, double
         return fail(AMC_ERR_VALUE, "rows [%lld, %lld) out of range 0..%lld", (long long)p0, (long long)p1, (long long)p->n_local);
     if (p1 == p0) return AMC_OK;
     amc_ctx* c = p->ctx;
+    if (!c) return fail(AMC_ERR_STATE, "the path set's context has been destroyed");
     CU(cudaSetDevice(c->device));
     const size_t bytes = (size_t)(p1 - p0) * (size_t)(p->n_steps + 1) * 8;
     int rc = ensure(c->misc, bytes);
     if (rc) return rc;
-    CU(launch_gather_rows(p->dtype, p->S, p->ld, p->n_steps + 1, p0, p1, (double*)c->misc.p, c->stream));
+    if (p->lean)
+        CU(launch_lean_walk(1, p->rounds, p->gen, p->path_offset >> 2, p->n_local, p->n_steps, p->n_steps, p0, p1, 0.0, nullptr,
+                            (double*)c->misc.p, nullptr, c->sm_count, c->stream));
+    else
+        CU(launch_gather_rows(p->dtype, p->S, p->ld, p->n_steps + 1, p0, p1, (double*)c->misc.p, c->stream));
     CU(cudaMemcpyAsync(out, c->misc.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return AMC_OK;
@@ -753,6 +921,9 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     int32_t* fh = barrier ? (int32_t*)c->first_hit.p : nullptr;
     if (first_hit_host && P > 0)
         CU(cudaMemcpyAsync(fh, first_hit_host, (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+    else if (barrier && P > 0 && p->lean)
+        CU(launch_lean_walk(2, p->rounds, p->gen, p->path_offset >> 2, P, n, n, 0, P, spec->barrier, nullptr, nullptr, fh,
+                            c->sm_count, c->stream));
     else if (barrier && P > 0)
         CU(launch_first_hit(dtype, p->S, p->ld, n + 1, P, spec->barrier, fh, c->stream));
 
@@ -903,6 +1074,118 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         return AMC_OK;
     };
 
+    // The persistent sweep (lsm_sweep.cuh) -- ONE cooperative launch whose blocks stay resident for all passes; the block
+    // that finishes a pass last reduces, exchanges and solves -- is what prices path-free sets (it regenerates the columns
+    // from the counters).  For stored sets the launch chain below is the default: measured on B200 the chain is faster
+    // on every workload (profiles/r2_persistent_vs_chain.md: the streaming loop needs the whole 64-register budget of 4
+    // blocks per SM; sweep-level state and the in-kernel solve spill).  AMC_PERSISTENT=1 selects it for stored sets too.
+    static const int opt_persistent = getenv("AMC_PERSISTENT") ? atoi(getenv("AMC_PERSISTENT")) : 0;
+    const bool persistent = C == 1 && (opt_persistent || p->lean) && (!exchange || c->transport == 2);
+    if (p->lean && !persistent)
+        return fail(AMC_ERR_STATE, "path-free sets need the persistent sweep (peer-memory transport when sharded)");
+    bool used_persistent = false;
+    if (persistent) {
+        used_persistent = true;
+        const int n_passes = regress ? n + 1 : 1;
+        const int lean = p->lean ? 1 : 0;
+        int& gcache = c->sweep_grid_cache[lean ? 3 : (sf32 ? 2 : dtype)][D];
+        if (gcache == 0) gcache = sweep_grid_size(dtype, sf32, D, lean, c->sm_count);
+        int64_t need = (P + 1023) / 1024;
+        if (need < 1) need = 1;
+        const int wgrid = (int)(need < gcache ? need : gcache);
+        if (getenv("AMC_SWEEP_DEBUG")) {
+            static int told = 0;
+            if (!told++) fprintf(stderr, "libamc sweep debug: cooperative grid %d (resident capacity %d on %d SMs), P=%lld\n", wgrid, gcache,
+                                 c->sm_count, (long long)P);
+        }
+        if (!c->ev_k0) {
+            CU(cudaEventCreate(&c->ev_k0));
+            CU(cudaEventCreate(&c->ev_k1));
+        }
+        if ((rc = ensure(c->partials, (size_t)wgrid * kAccStride * 8))) return rc;
+        const size_t sync_bytes = (size_t)(kSyncTickets + n_passes + 32) * 4;
+        if ((rc = ensure(c->syncbuf, sync_bytes))) return rc;
+        const size_t tab_bytes = nrow * (sizeof(SweepTab) + sizeof(SolverTab));
+        if ((rc = ensure(c->tabs, tab_bytes))) return rc;
+        std::vector<unsigned char> tab_h(tab_bytes);
+        SweepTab* wt = (SweepTab*)tab_h.data();
+        SolverTab* st = (SolverTab*)(tab_h.data() + nrow * sizeof(SweepTab));
+        for (int t = 0; t <= n; ++t) {
+            wt[t].disc = exp(-rdt * (double)t);
+            wt[t].mu = p->mu[t];
+            wt[t].isg = 1.0 / p->sigma[t];
+            wt[t].pad = 0.0;
+            st[t].y_scale = exp(rdt * (double)t);
+            st[t].mu = p->mu[t];
+            st[t].sigma = 1.0 / (1.0 / p->sigma[t]);       // the scale the kernels effectively use
+            st[t].pad = 0.0;
+        }
+        CU(cudaMemcpyAsync(c->tabs.p, tab_h.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync(c->syncbuf.p, 0, sync_bytes, c->stream));
+        int32_t* Lstate = nullptr;
+        if (lean) {
+            if ((rc = ensure(c->lstate, (size_t)ldp * 4))) return rc;
+            Lstate = (int32_t*)c->lstate.p;
+            CU(cudaMemcpyAsync(Lstate, p->Ln, (size_t)ldp * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
+
+        SweepArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.S = p->S;
+        wa.ld = p->ld;
+        wa.L = Lstate;
+        wa.U = c->U.p;
+        wa.tau = tau;
+        wa.first_hit = fh;
+        wa.tab = (const SweepTab*)c->tabs.p;
+        wa.gamma = dg + off_gamma;
+        wa.partials = (double*)c->partials.p;
+        wa.sync = (uint32_t*)c->syncbuf.p;
+        wa.n_paths = P;
+        wa.n_steps = n;
+        wa.n_passes = n_passes;
+        wa.american = american ? 1 : 0;
+        wa.is_put = spec->is_put;
+        wa.reverse = opt_reverse;
+        wa.K = spec->K;
+        wa.gen = p->gen;
+        wa.quad0 = p->path_offset >> 2;
+        wa.rounds = p->rounds;
+
+        SolveArgs& so = wa.solve;
+        so.partials = (const double*)c->partials.p;
+        so.n_rows = wgrid;
+        so.sums = (double*)c->sums.p;
+        so.spec = sspec;
+        // inside the sweep kernel the scalar routine runs under the streaming loop's register cap (it spills): the
+        // warp-cooperative routine takes every step it can certify, at every degree
+        if (opt_warp_solve < 0) so.spec.warp_solve = 1;
+        so.gamma = dg + off_gamma;
+        so.beta = dg + off_beta;
+        so.sv = dg + off_sv;
+        so.mean_std = dg + off_ms;
+        so.rank = drank;
+        so.price = dg + off_price;
+        so.n_batch = 1;
+        so.gamma_stride = (int64_t)nrow * kMaxK;
+        if (exchange) {
+            for (int q = 0; q < c->world; ++q) so.peer.mailbox[q] = (uint4*)c->peer_mailbox[q];
+            so.peer.world = c->world;
+            so.peer.rank = c->rank;
+            so.peer.err = c->peer_err;
+            if (c->peer_seq > 0xFFF00000u) c->peer_seq = 0;        // same rule on every rank; a sequence number is never 0
+            wa.seq_base = c->peer_seq;
+            c->peer_seq += (uint32_t)n_passes;
+        }
+        wa.solve_tab = (const SolverTab*)((const char*)c->tabs.p + nrow * sizeof(SweepTab));
+
+        CU(cudaEventRecord(c->ev_k0, c->stream));
+        CU(launch_sweep(dtype, sf32, D, lean, wgrid, wa, c->stream));
+        CU(cudaEventRecord(c->ev_k1, c->stream));
+        n_step = 1;
+        n_solve = 0;
+    } else
+    {
     if (!regress) {
         // no early exercise and nobody wants continuation values: the price is the discounted mean payoff
         if ((rc = run_step(n, kMaturity, false))) return rc;
@@ -957,6 +1240,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
             if ((rc = enqueue_plan())) return rc;
         }
     }
+    }
     CU(cudaEventRecord(ev_stop, c->stream));
 
     CU(cudaMemcpyAsync(price, dg + off_price, 8 * (size_t)C, cudaMemcpyDeviceToHost, c->stream));
@@ -982,8 +1266,25 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         }
     }
     int peer_err_h = 0;
+    uint32_t abort_h = 0;
     if (exchange && c->transport == 2) CU(cudaMemcpyAsync(&peer_err_h, c->peer_err, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (used_persistent)
+        CU(cudaMemcpyAsync(&abort_h, (uint32_t*)c->syncbuf.p + kSyncAbort, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (exchange && c->transport == 1) {
+        if ((rc = sync_with_nccl_watchdog(c))) return rc;
+    } else {
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (abort_h && getenv("AMC_SWEEP_DEBUG")) {
+        std::vector<uint32_t> w(kSyncTickets + 8);
+        cudaMemcpy(w.data(), c->syncbuf.p, w.size() * 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "libamc sweep debug: published=%u abort=%u tickets=%u %u %u %u (P=%lld n=%d D=%d dtype=%d sf32=%d)\n",
+                w[kSyncPublished], w[kSyncAbort], w[kSyncTickets], w[kSyncTickets + 1], w[kSyncTickets + 2],
+                w[kSyncTickets + 3], (long long)P, n, D, dtype, sf32);
+    }
+    if (abort_h && !peer_err_h)
+        return fail(AMC_ERR_CUDA, "the persistent sweep timed out waiting for one of its own passes; AMC_PERSISTENT=0 selects the "
+                                  "per-step launch chain");
     if (peer_err_h) {
         cudaMemsetAsync(c->peer_err, 0, 4, c->stream);
         return fail(AMC_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not reach the same step of the sweep");
@@ -1013,6 +1314,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
             CU(cudaEventElapsedTime(&ms, solve_ev[i], solve_ev[i + 1]));
             timing->solve_kernel_ms += ms;
         }
+        if (used_persistent) CU(cudaEventElapsedTime(&timing->step_kernel_ms, c->ev_k0, c->ev_k1));
         timing->step_launches = n_step;
         timing->solve_launches = n_solve;
         timing->other_launches = n_other;
@@ -1052,13 +1354,18 @@ extern "C" int amc_paths_gather_steps(const amc_paths* p, const int32_t* steps, 
     if (!p || !steps || !out) return fail(AMC_ERR_VALUE, "amc_paths_gather_steps: null argument");
     if (p->n_local == 0) return AMC_OK;
     amc_ctx* c = p->ctx;
+    if (!c) return fail(AMC_ERR_STATE, "the path set's context has been destroyed");
     CU(cudaSetDevice(c->device));
     int rc = ensure(c->misc, (size_t)p->n_local * 12);
     if (rc) return rc;
     double* out_dev = (double*)c->misc.p;
     int32_t* st_dev = (int32_t*)(out_dev + p->n_local);
     CU(cudaMemcpyAsync(st_dev, steps, (size_t)p->n_local * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(launch_gather_steps(p->dtype, p->S, p->ld, p->n_steps + 1, p->n_local, st_dev, out_dev, c->stream));
+    if (p->lean)
+        CU(launch_lean_walk(3, p->rounds, p->gen, p->path_offset >> 2, p->n_local, p->n_steps, p->n_steps, 0, p->n_local, 0.0,
+                            st_dev, out_dev, nullptr, c->sm_count, c->stream));
+    else
+        CU(launch_gather_steps(p->dtype, p->S, p->ld, p->n_steps + 1, p->n_local, st_dev, out_dev, c->stream));
     CU(cudaMemcpyAsync(out, out_dev, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return AMC_OK;
@@ -1070,6 +1377,7 @@ extern "C" int amc_lsm_price_batch(amc_ctx* c, const amc_paths* p, const amc_lsm
     if (p->ctx != c) return fail(AMC_ERR_STATE, "amc_lsm_price_batch: path set belongs to another context");
     if (n_contracts < 1 || n_contracts > AMC_MAX_BATCH)
         return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: n_contracts %d outside 1..%d", n_contracts, AMC_MAX_BATCH);
+    if (p->lean) return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: path-free sets are priced one contract at a time (amc_lsm_price)");
     if (p->n_global != p->n_local)
         return fail(AMC_ERR_VALUE, "amc_lsm_price_batch: the path set is sharded over ranks; batches are sharded by "
                                    "contract (every rank prices its own contracts on its own complete path sets)");
@@ -1106,8 +1414,16 @@ extern "C" int amc_continuation(amc_ctx* c, const amc_paths* p, int t, const dou
     double* out_dev = (double*)c->misc.p;
     double* gam_dev = out_dev + p->n_local;
     CU(cudaMemcpyAsync(gam_dev, gamma, (size_t)(degree + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(launch_continuation(p->dtype, column(p, t), p->n_local, gam_dev, degree, p->mu[t], 1.0 / p->sigma[t], 1, out_dev,
-                           c->stream));
+    if (p->lean) {
+        if ((rc = ensure(c->lstate, (size_t)p->n_local * 8))) return rc;
+        CU(launch_lean_walk(0, p->rounds, p->gen, p->path_offset >> 2, p->n_local, p->n_steps, t, 0, p->n_local, 0.0, nullptr,
+                            (double*)c->lstate.p, nullptr, c->sm_count, c->stream));
+        CU(launch_continuation(AMC_F64, c->lstate.p, p->n_local, gam_dev, degree, p->mu[t], 1.0 / p->sigma[t], 1, out_dev,
+                               c->stream));
+    } else {
+        CU(launch_continuation(p->dtype, column(p, t), p->n_local, gam_dev, degree, p->mu[t], 1.0 / p->sigma[t], 1, out_dev,
+                               c->stream));
+    }
     CU(cudaMemcpyAsync(out, out_dev, (size_t)p->n_local * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return AMC_OK;
@@ -1167,8 +1483,16 @@ extern "C" int amc_ccr_exposures(amc_ctx* c, const amc_paths* p, const double* g
     for (int t = 0; t <= n; ++t) {
         CcrSource src;
         memset(&src, 0, sizeof(src));
-        src.x = column(p, t);
-        src.x_f32 = p->dtype == AMC_F32;
+        if (p->lean) {                                  // materialise the column (walks the counters forward to step t)
+            if ((rc = ensure(c->lstate, (size_t)p->n_local * 8))) return rc;
+            CU(launch_lean_walk(0, p->rounds, p->gen, p->path_offset >> 2, p->n_local, n, t, 0, p->n_local, 0.0, nullptr,
+                                (double*)c->lstate.p, nullptr, c->sm_count, c->stream));
+            src.x = c->lstate.p;
+            src.x_f32 = 0;
+        } else {
+            src.x = column(p, t);
+            src.x_f32 = p->dtype == AMC_F32;
+        }
         src.degree = degree;
         src.clamp = 1;                                  // np.maximum(fit, 0), amc.py:132
         src.zero = (t == n);                            // amc.py:145: zeros at maturity
@@ -1253,7 +1577,7 @@ static int regression_fit_impl(amc_ctx* c, const double* X, const double* Y, Pre
     CU(cudaSetDevice(c->device));
     // a one-column path set holding X; Y plays the role of the per-path state
     amc_paths* px = nullptr;
-    if ((rc = paths_alloc(c, 0, n, n, AMC_F64, &px))) return rc;
+    if ((rc = paths_alloc(c, 0, n, n, AMC_F64, &px, kPathBorrowed))) return rc;
     auto cleanup = [&](int code) { amc_paths_free(px); return code; };
     cudaError_t e = cudaMemcpyAsync(px->S, X, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) return cleanup(fail(AMC_ERR_CUDA, "H2D X: %s", cudaGetErrorString(e)));
@@ -1388,9 +1712,59 @@ extern "C" int amc_barrier_hit_matrix(amc_ctx* c, const amc_paths* p, double bar
     int rc = ensure(c->first_hit, (size_t)padded_len(p->n_local) * 4);
     if (rc) return rc;
     if ((rc = ensure(c->misc, total))) return rc;
-    CU(launch_first_hit(p->dtype, p->S, p->ld, p->n_steps + 1, p->n_local, barrier, (int32_t*)c->first_hit.p, c->stream));
+    if (p->lean)
+        CU(launch_lean_walk(2, p->rounds, p->gen, p->path_offset >> 2, p->n_local, p->n_steps, p->n_steps, 0, p->n_local,
+                            barrier, nullptr, nullptr, (int32_t*)c->first_hit.p, c->sm_count, c->stream));
+    else
+        CU(launch_first_hit(p->dtype, p->S, p->ld, p->n_steps + 1, p->n_local, barrier, (int32_t*)c->first_hit.p, c->stream));
     CU(launch_hit_matrix((const int32_t*)c->first_hit.p, p->n_steps + 1, p->n_local, (uint8_t*)c->misc.p, c->stream));
     CU(cudaMemcpyAsync(out, c->misc.p, total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generator self-tests (see pathgen.cu)
+extern "C" int amc_selftest_philox(amc_ctx* c, int rounds, const uint32_t* counters, const uint32_t key[2], int n,
+                                   uint32_t* out) {
+    if (!c || !counters || !key || !out || n < 0) return fail(AMC_ERR_VALUE, "amc_selftest_philox: bad argument");
+    if (rounds != 10 && rounds != 7) return fail(AMC_ERR_VALUE, "amc_selftest_philox: rounds must be 10 or 7");
+    if (n == 0) return AMC_OK;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure(c->misc, (size_t)n * 32);
+    if (rc) return rc;
+    uint32_t* ctr_dev = (uint32_t*)c->misc.p;
+    uint32_t* out_dev = ctr_dev + (size_t)n * 4;
+    CU(cudaMemcpyAsync(ctr_dev, counters, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_philox_kat(rounds, ctr_dev, key[0], key[1], n, out_dev, c->stream));
+    CU(cudaMemcpyAsync(out, out_dev, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_selftest_normals(amc_ctx* c, int rounds, uint64_t seed, int64_t n_quads, int n_steps, int n_bins,
+                                    double lo, double hi, uint64_t* hist, double stats[6]) {
+    if (!c || !hist || !stats || n_quads < 0 || n_steps < 1)
+        return fail(AMC_ERR_VALUE, "amc_selftest_normals: bad argument");
+    if (rounds != 10 && rounds != 7) return fail(AMC_ERR_VALUE, "amc_selftest_normals: rounds must be 10 or 7");
+    if (n_bins < 1 || n_bins > 4096 || !(hi > lo)) return fail(AMC_ERR_VALUE, "amc_selftest_normals: 1..4096 bins on [lo, hi)");
+    CU(cudaSetDevice(c->device));
+    const int grid = c->sm_count * 4;
+    const size_t hist_bytes = (size_t)(n_bins + 2) * 8;
+    int rc = ensure(c->misc, hist_bytes + (size_t)grid * 6 * 8);
+    if (rc) return rc;
+    unsigned long long* hist_dev = (unsigned long long*)c->misc.p;
+    double* stats_dev = (double*)((char*)c->misc.p + hist_bytes);
+    CU(cudaMemsetAsync(c->misc.p, 0, hist_bytes + (size_t)grid * 6 * 8, c->stream));
+    CU(launch_normals_hist(rounds, seed, n_quads, n_steps, n_bins, lo, hi, hist_dev, stats_dev, grid, c->stream));
+    std::vector<double> st((size_t)grid * 6);
+    CU(cudaMemcpyAsync(hist, hist_dev, hist_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(st.data(), stats_dev, st.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < 6; ++j) stats[j] = 0.0;
+    for (int b = 0; b < grid; ++b) {
+        for (int j = 0; j < 5; ++j) stats[j] += st[(size_t)b * 6 + j];
+        if (st[(size_t)b * 6 + 5] > stats[5]) stats[5] = st[(size_t)b * 6 + 5];
+    }
     return AMC_OK;
 }

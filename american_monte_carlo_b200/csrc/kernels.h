@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gbm_quad.cuh"
 #include "lsm_solve.h"
 
 namespace amc {
@@ -92,6 +93,58 @@ struct SolveArgs {
     PeerArgs peer;
 };
 
+// ---- persistent one-launch sweep (lsm_sweep.cuh) ---------------------------------------------------------------
+struct SweepTab {             // per column t
+    double disc;              // exp(-r dt t)
+    double mu, isg;           // affine map  z = (x - mu) * isg
+    double pad;
+};
+
+// sync words (uint32), each group on its own 128-byte line
+constexpr int kSyncPublished = 0;      // number of solves published
+constexpr int kSyncAbort = 32;         // nonzero: somebody timed out, everybody leaves
+constexpr int kSyncTickets = 64;       // [n_passes]: blocks done with pass p
+constexpr unsigned long long kSpinLimitNs = 8000000000ull;
+
+struct SolverTab {            // per regressed column t
+    double y_scale;           // exp(r dt t): brings the time-0 cashflows to time t
+    double mu, sigma;         // affine map of the column
+    double pad;
+};
+
+struct SweepArgs {
+    const void* S;            // path matrix, timestep-major (column t at S + t * ld); null in LEAN mode
+    int64_t ld;
+    int32_t* L;               // LEAN: log2-price state, in: L_n, rewritten every pass
+    void* U;
+    int32_t* tau;
+    const int32_t* first_hit;
+    const SweepTab* tab;      // [n+1]
+    const double* gamma;      // [n+1][kMaxK], row t written by the solver before pass n-t
+    double* partials;         // [gridDim.x][kAccStride]
+    uint32_t* sync;
+    int64_t n_paths;
+    int n_steps;
+    int n_passes;             // n+1 with regressions, 1 without (price = discounted mean payoff)
+    int american;
+    int is_put;
+    int reverse;              // alternate the tile direction from pass to pass (L2: the tail of pass p is the head of p+1)
+    double K;
+    QuadGen gen;              // LEAN
+    int64_t quad0;            // LEAN: global quad id of local path 0 (path_offset / 4)
+    int rounds;               // LEAN: Philox rounds the path set was generated with (10 or 7)
+    // the solve of every pass is done by whichever block finishes the pass last (lsm_solve_block.cuh)
+    SolveArgs solve;          // spec, partials, n_rows, sums, peer; gamma / beta / sv / mean_std / rank / price = TABLE bases
+    const SolverTab* solve_tab;   // [n+1]
+    uint32_t seq_base;        // multi-GPU: pass p exchanges under sequence number seq_base + p + 1
+};
+
+
+// grid of the cooperative launch: SM count x resident blocks per SM (every block resident: they wait on each other)
+int sweep_grid_size(int dtype, int state_f32, int degree, int lean, int sm_count);
+cudaError_t launch_sweep(int dtype, int state_f32, int degree, int lean, int grid, const SweepArgs& a, cudaStream_t s);
+
+
 int step_grid_size(int dtype, int state_f32, int degree, int sm_count);
 // pdl: launch as a programmatic dependent of the previous kernel in the stream (see common.cuh)
 cudaError_t launch_step(int dtype, int state_f32, int degree, int grid, const StepArgs& a, cudaStream_t s,
@@ -135,8 +188,19 @@ cudaError_t launch_ccr_scan(SelState* st, unsigned long long* hist, int pass, co
 struct GbmParams {
     double S0, drift, vol;     // per-step log drift (r - sigma^2/2) dt and vol sigma sqrt(dt)
 };
-cudaError_t launch_generate_philox(int dtype, void* S, int64_t ld, int n_steps, int64_t n_local, int64_t path_offset,
-                                   GbmParams g, uint64_t seed, int sm_count, cudaStream_t s);
+QuadGen make_quad_gen(const GbmParams& g, int n_steps, uint64_t seed);
+int philox_rounds();      // 10, or 7 with AMC_PHILOX_ROUNDS=7 (float generator only; philox.cuh)
+cudaError_t launch_generate_philox(int dtype, void* S, int32_t* L_out, int64_t ld, int n_steps, int64_t n_local,
+                                   int64_t path_offset, GbmParams g, uint64_t seed, int sm_count, cudaStream_t s);
+// lean (path-free) sets: mode 0 = column t_stop -> out[n_local], 1 = rows [p_lo, p_hi) -> out[(p_hi-p_lo)][n+1],
+// 2 = first knock-in step -> out_i[n_local], 3 = out[p] = S[steps[p]][p]; all by walking forward from the counters
+cudaError_t launch_lean_walk(int mode, int rounds, const QuadGen& g, int64_t quad0, int64_t n_local, int n_steps, int t_stop,
+                             int64_t p_lo, int64_t p_hi, double barrier, const int32_t* steps_dev, double* out_dev,
+                             int32_t* out_i_dev, int sm_count, cudaStream_t s);
+cudaError_t launch_philox_kat(int rounds, const uint32_t* ctr_dev, uint32_t k0, uint32_t k1, int n, uint32_t* out_dev,
+                              cudaStream_t s);
+cudaError_t launch_normals_hist(int rounds, uint64_t seed, int64_t n_quads, int n_steps, int n_bins, double lo, double hi,
+                                unsigned long long* hist_dev, double* stats_dev, int grid, cudaStream_t s);
 cudaError_t launch_from_normals(int dtype, const double* Z_dev, void* S, int64_t ld, int n_steps, int64_t n_local,
                                 GbmParams g, cudaStream_t s);
 cudaError_t launch_transpose_in(int dtype, const double* S_rowmajor_dev, void* S, int64_t ld, int n_cols,

@@ -5,7 +5,8 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.cuh"
-#include "lsm_solve_warp.cuh"
+#include "lsm_solve_block.cuh"
+#include "lsm_sweep.cuh"
 
 namespace amc {
 
@@ -15,6 +16,14 @@ cudaError_t launch_step_f32s(int degree, int grid, const StepArgs& a, cudaStream
 int step_occupancy_f32(int degree);
 int step_occupancy_f64(int degree);
 int step_occupancy_f32s(int degree);
+cudaError_t launch_sweep_f32(int degree, int grid, const SweepArgs& a, cudaStream_t s);
+cudaError_t launch_sweep_f64(int degree, int grid, const SweepArgs& a, cudaStream_t s);
+cudaError_t launch_sweep_f32s(int degree, int grid, const SweepArgs& a, cudaStream_t s);
+cudaError_t launch_sweep_lean(int state_f32, int degree, int grid, const SweepArgs& a, cudaStream_t s);
+int sweep_occupancy_f32(int degree);
+int sweep_occupancy_f64(int degree);
+int sweep_occupancy_f32s(int degree);
+int sweep_occupancy_lean(int state_f32, int degree);
 
 // ---------------------------------------------------------------------------------------------------------
 // Solve kernel: <<<1, 128>>>.
@@ -23,8 +32,6 @@ int step_occupancy_f32s(int degree);
 //   phase 2 (do_solve):  thread 0 runs the k x k solve and stores gamma / diagnostics.
 //   final_price:         price = sum(U) / P.
 // Multi-GPU: phase 1, then an NCCL all-reduce of `sums`, then phase 2 as a second launch.
-constexpr int kSolveThreads = 256;
-
 template <int K>
 __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const SolveArgs a_in) {
     SolveArgs a = a_in;
@@ -36,120 +43,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
         a.price = a_in.price + c;
         a.beta = nullptr; a.sv = nullptr; a.mean_std = nullptr; a.rank = nullptr;
     }
-    constexpr int d = K - 1;
-    constexpr int nacc = 3 * d + 1;
-    __shared__ double part[kSolveThreads / 32][kAccStride];
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     pdl_launch_dependents();
     pdl_wait();
-    if (a.do_reduce) {
-        // A partial row is 32 doubles of which the first nacc are used: LPR lanes read one row, so a warp covers
-        // 32 / LPR rows per load.  Every thread issues 16 independent (predicated) loads per round: the latency of the
-        // L2-resident partials is paid ceil(rows / (16 * slots)) times -- 3 rounds for a full grid -- not once per row.
-        // Summation order is fixed (slot, then rows ascending, then slots ascending): deterministic.
-        constexpr int LPR = nacc <= 8 ? 8 : (nacc <= 16 ? 16 : 32);
-        constexpr int RPW = 32 / LPR;
-        constexpr int NSLOT = (kSolveThreads / 32) * RPW;
-        const int col = lane % LPR;
-        const int slot = grp * RPW + lane / LPR;
-        // contract batches: the power sums (columns < 2d) are taken from contract 0's rows (see lsm_step.cuh)
-        const double* src = (col < 2 * d) ? a_in.partials : a.partials;
-        double v = 0.0;
-        for (int row0 = slot; row0 < a.n_rows; row0 += 16 * NSLOT) {
-            double t[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int r = row0 + q * NSLOT;
-                t[q] = (r < a.n_rows) ? src[(int64_t)r * kAccStride + col] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v += t[q];
-        }
-        double* flat = &part[0][0];                       // [NSLOT][LPR] = 256 doubles
-        flat[slot * LPR + col] = v;
-        __syncthreads();
-        double tot = 0.0;
-        if (threadIdx.x < nacc) {
-#pragma unroll
-            for (int q = 0; q < NSLOT; ++q) tot += flat[q * LPR + threadIdx.x];
-        }
-        __syncthreads();
-        if (threadIdx.x < nacc) {
-            a.sums[threadIdx.x] = tot;
-            part[0][threadIdx.x] = tot;
-        }
-        __syncthreads();
-    } else {
-        if (threadIdx.x < nacc) part[0][threadIdx.x] = a.sums[threadIdx.x];
-        __syncthreads();
-    }
-    if (a.peer.world > 1) {
-        // fused all-reduce over peer memory: push this rank's sums into everybody's mailbox, then gather
-        const int W = a.peer.world;
-        __shared__ uint32_t s_seq;
-        if (threadIdx.x == 0) {
-            uint32_t v = atomicAdd(a.peer.seq_ctr, 1u) + 1u;
-            if (v == 0u) v = atomicAdd(a.peer.seq_ctr, 1u) + 1u;      // 0 marks a never-written cell
-            s_seq = v;
-        }
-        __syncthreads();
-        const uint32_t seq = s_seq;
-        const int slot = (int)(seq % kPeerRing);
-        for (int idx = threadIdx.x; idx < W * nacc; idx += kSolveThreads) {
-            const int q = idx / nacc, i = idx - q * nacc;
-            st_ll(a.peer.mailbox[q] + ((slot * W + a.peer.rank) * kAccStride + i), part[0][i], seq);
-        }
-        double tot = 0.0;
-        if (threadIdx.x < nacc) {
-            const uint4* mine = a.peer.mailbox[a.peer.rank] + (slot * W) * kAccStride + threadIdx.x;
-            const uint64_t t0 = global_timer_ns();
-            for (int q = 0; q < W; ++q) {                  // rank order: identical bits on every rank
-                double v;
-                int spins = 0;
-                while (!ld_ll(mine + q * kAccStride, seq, v)) {
-                    if (((++spins) & 1023) == 0 && global_timer_ns() - t0 > 4000000000ull) {   // 4 s: a peer is gone
-                        *a.peer.err = 1;
-                        v = 0.0;
-                        break;
-                    }
-                }
-                tot += v;
-            }
-        }
-        __syncthreads();                                   // every thread has read part[0][*] for its pushes
-        if (threadIdx.x < nacc) {
-            part[0][threadIdx.x] = tot;
-            a.sums[threadIdx.x] = tot;
-        }
-        __syncthreads();
-    }
-    if (a.final_price) {
-        if (threadIdx.x == 0) a.price[0] = part[0][2 * d] / a.spec.n_paths;
-        return;
-    }
-    if (!a.do_solve || threadIdx.x >= 32) return;
-    // warp 0: cooperative solve of the certified full-rank case; everything else (degenerate column, rank truncation,
-    // SVD diagnostics) falls through to the scalar routine on thread 0
-    __shared__ SolveShared<K> solve_sh;
-    const bool solved = lsm_solve_warp<K>(a.spec, &part[0][0], &part[0][2 * d], a.y_scale, a.mu_ref, a.sigma_ref, solve_sh,
-                                          a.gamma, a.beta, a.sv, a.mean_std, a.rank);
-    if (solved || threadIdx.x != 0) return;
-    double h[2 * d + 1], g[K];
-    h[0] = a.spec.n_paths;
-#pragma unroll
-    for (int m = 1; m <= 2 * d; ++m) h[m] = part[0][m - 1];
-#pragma unroll
-    for (int m = 0; m <= d; ++m) g[m] = part[0][2 * d + m];
-    SolveResult res;
-    lsm_solve_t<K>(a.spec, h, g, a.y_scale, a.mu_ref, a.sigma_ref, &res);
-#pragma unroll
-    for (int i = 0; i < kMaxK; ++i) {
-        a.gamma[i] = res.gamma[i];
-        if (a.beta) a.beta[i] = res.beta[i];
-        if (a.sv) a.sv[i] = res.sv[i];
-    }
-    if (a.mean_std) { a.mean_std[0] = res.mean_x; a.mean_std[1] = res.std_x; a.mean_std[2] = res.pivot_loss; }
-    if (a.rank) a.rank[0] = res.rank;
+    solve_block<K>(a, a_in, 0u, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -235,6 +131,21 @@ int step_grid_size(int dtype, int state_f32, int degree, int sm_count) {
     int nb = dtype == 1 ? (state_f32 ? step_occupancy_f32s(degree) : step_occupancy_f32(degree)) : step_occupancy_f64(degree);
     if (nb < 1) nb = 1;
     return sm_count * nb;
+}
+
+cudaError_t launch_sweep(int dtype, int state_f32, int degree, int lean, int grid, const SweepArgs& a, cudaStream_t s) {
+    if (lean) return dtype == 1 ? launch_sweep_lean(state_f32, degree, grid, a, s) : cudaErrorInvalidValue;
+    if (dtype == 1 && state_f32) return launch_sweep_f32s(degree, grid, a, s);
+    if (state_f32) return cudaErrorInvalidValue;
+    return dtype == 1 ? launch_sweep_f32(degree, grid, a, s) : launch_sweep_f64(degree, grid, a, s);
+}
+
+int sweep_grid_size(int dtype, int state_f32, int degree, int lean, int sm_count) {
+    int nb;
+    if (lean) nb = sweep_occupancy_lean(state_f32, degree);
+    else nb = dtype == 1 ? (state_f32 ? sweep_occupancy_f32s(degree) : sweep_occupancy_f32(degree)) : sweep_occupancy_f64(degree);
+    if (nb < 1) nb = 1;
+    return sm_count * nb;                                  // cooperative launch: every block resident
 }
 
 cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl) {

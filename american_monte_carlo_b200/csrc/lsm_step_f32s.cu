@@ -1,5 +1,5 @@
 // Step kernels for float path storage, float state (all degrees); see lsm_step.cuh.
-#include "lsm_step.cuh"
+#include "lsm_sweep.cuh"
 
 namespace amc {
 
@@ -8,5 +8,11 @@ cudaError_t launch_step_f32s(int degree, int grid, const StepArgs& a, cudaStream
 }
 
 int step_occupancy_f32s(int degree) { return occupancy_d<float, float>(degree); }
+
+cudaError_t launch_sweep_f32s(int degree, int grid, const SweepArgs& a, cudaStream_t s) {
+    return launch_sweep_d<float, float, false>(degree, grid, a, s);
+}
+
+int sweep_occupancy_f32s(int degree) { return sweep_occupancy_d<float, float, false>(degree); }
 
 }  // namespace amc

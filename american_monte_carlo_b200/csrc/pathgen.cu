@@ -12,91 +12,71 @@
 //                          into timestep-major coalesced writes.  The A/B mode against the reference.
 //   transpose_in_kernel  : adopt a reference-layout path matrix S[p][t].
 // plus column statistics, the knock-in index of the down-and-in barrier (amc.py:171-176) and read-back helpers.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "gbm_quad.cuh"
 #include "philox.cuh"
 
 namespace amc {
 
 // ---------------------------------------------------------------------------------------------------------
-// K1, f32 storage: 4 adjacent paths per thread, 4 steps per Philox call and path.  Everything stays on the FP32 /
-// integer / MUFU pipes (no f32<->f64 conversions, no FP64 adds): the cumulative log-price is a Kahan-compensated float
-// sum kept in log2 units, so each step costs one FFMA + four FADD for the sum and one MUFU.EX2 + one FMUL for the
-// price.  Accuracy: the compensated sum is good to ~1e-8 in the exponent, below the 6e-8 rounding of the float the
-// price is stored in; the float-rounded step constants (drift, vol) are off by < 3e-8 relative, ~1e-8 on the price.
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sin_approx(float x) {
-    float y;
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float cos_approx(float x) {
-    float y;
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__global__ void __launch_bounds__(256) philox_paths_f32_kernel(float* __restrict__ S, int64_t ld, int n_steps,
-                                                               int64_t n_local, int64_t path_offset, GbmParams g,
-                                                               uint32_t k0, uint32_t k1) {
-    const int64_t n_vec = (n_local + 3) >> 2;
-    const float S0f = (float)g.S0;
-    const float d2 = (float)(g.drift * 1.4426950408889634), v2 = (float)(g.vol * 1.4426950408889634);   // log2 units
-    const float neg2ln2 = -1.3862943611198906f;             // -2 ln u = (-2 ln 2) log2 u
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p0 = v << 2;
-        float L[4] = {0.f, 0.f, 0.f, 0.f}, C[4] = {0.f, 0.f, 0.f, 0.f};
+// K1, f32 storage: one thread = one QUAD of four adjacent paths, walked through all n steps; one Philox call per quad
+// and step (gbm_quad.cuh), the log2-prices kept as exact int32 fixed-point sums, one 128-bit streaming store per
+// thread and step.  FP32 / integer / MUFU pipes only.  Per path-step: 10 (Philox-10) + 5 (Box-Muller) + 6 (sum, price)
+// instructions, 3 MUFU ops.
+//   S == nullptr: nothing is stored per step (path-free mode, amc_paths_generate_lean): only the terminal log-prices
+//   L_n go to `L_out` -- the backward sweep regenerates every earlier column from them.
+template <int ROUNDS, bool ALIGNED>
+__global__ void __launch_bounds__(256) philox_quads_f32_kernel(float* __restrict__ S, int32_t* __restrict__ L_out,
+                                                               int64_t ld, int n_steps, int64_t n_local,
+                                                               int64_t path_offset, QuadGen g) {
+    const int64_t quad0 = path_offset >> 2;                        // first global quad that holds a local path
+    const int shift = (int)(path_offset & 3);                      // ALIGNED: 0
+    const int64_t n_quads = ((path_offset + n_local + 3) >> 2) - quad0;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_quads; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t quad = (uint64_t)(quad0 + v);
+        const uint32_t qlo = (uint32_t)quad, qhi = (uint32_t)(quad >> 32);
+        const int64_t p0 = (v << 2) - shift;                       // local index of the quad's first path (may be < 0)
+        int L[4] = {0, 0, 0, 0};
+        if (S) {
+            if (ALIGNED) {
+                st_stream(reinterpret_cast<float4*>(S + p0), make_float4(g.S0, g.S0, g.S0, g.S0));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (p0 + i >= 0 && p0 + i < n_local) S[p0 + i] = g.S0;
+            }
+        }
         float* out_col = S + p0;
-        st_stream(reinterpret_cast<float4*>(out_col), make_float4(S0f, S0f, S0f, S0f));
-        for (int t0 = 0; t0 < n_steps; t0 += 4) {
-            float z[4][4];
+        for (int t = 1; t <= n_steps; ++t) {
+            int q[4];
+            quad_increments<ROUNDS>(g, qlo, qhi, (uint32_t)t, q);
+            float out[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint64_t gid = (uint64_t)(path_offset + p0 + i);
-                const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(t0 >> 2),
-                                                kPhiloxDomain, k0, k1);
+                L[i] += q[i];
+                out[i] = price_from_log(g, L[i]);
+            }
+            if (S) {
+                out_col += ld;
+                if (ALIGNED) {
+                    st_stream(reinterpret_cast<float4*>(out_col), make_float4(out[0], out[1], out[2], out[3]));
+                } else {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    // u1 in (0, 1]: full 32-bit resolution in the tail (small integers convert exactly)
-                    const float u1 = fmaf((float)r.v[2 * h], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-                    const float rad = sqrt_approx(neg2ln2 * lg2_approx(u1));
-                    // angle: the low 23 bits become the mantissa of a float in [1, 2) (one LOP3, no int->float
-                    // conversion on the MUFU pipe); 2 pi f - 3 pi lies in [-pi, pi)
-                    const float f12 = __uint_as_float((r.v[2 * h + 1] & 0x007fffffu) | 0x3f800000u);
-                    const float ang = fmaf(f12, 6.283185307179586f, -9.42477796076938f);
-                    z[i][2 * h] = rad * cos_approx(ang);
-                    z[i][2 * h + 1] = rad * sin_approx(ang);
+                    for (int i = 0; i < 4; ++i)
+                        if (p0 + i >= 0 && p0 + i < n_local) out_col[i] = out[i];
                 }
             }
+        }
+        if (L_out) {
+            if (ALIGNED) {
+                *reinterpret_cast<int4*>(L_out + p0) = make_int4(L[0], L[1], L[2], L[3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (t0 + j < n_steps) {
-                    out_col += ld;
-                    float out[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float y = fmaf(v2, z[i][j], d2) - C[i];        // Kahan: carry the rounding of the sum
-                        const float t = L[i] + y;
-                        C[i] = (t - L[i]) - y;
-                        L[i] = t;
-                        out[i] = S0f * ex2_approx(t);
-                    }
-                    st_stream(reinterpret_cast<float4*>(out_col), make_float4(out[0], out[1], out[2], out[3]));
-                }
+                for (int i = 0; i < 4; ++i)
+                    if (p0 + i >= 0 && p0 + i < n_local) L_out[p0 + i] = L[i];
             }
         }
     }
@@ -141,18 +121,228 @@ __global__ void __launch_bounds__(256) philox_paths_f64_kernel(double* __restric
     }
 }
 
-cudaError_t launch_generate_philox(int dtype, void* S, int64_t ld, int n_steps, int64_t n_local, int64_t path_offset,
-                                   GbmParams g, uint64_t seed, int sm_count, cudaStream_t s) {
+QuadGen make_quad_gen(const GbmParams& g, int n_steps, uint64_t seed) {
+    const double log2e = 1.4426950408889634;
+    const double d2 = g.drift * log2e, v2 = fabs(g.vol) * log2e;     // log2 units; -z is as normal as z
+    QuadGen q;
+    q.k = fixed_point_bits(d2, v2, n_steps);
+    const double sc = ldexp(1.0, q.k);
+    q.kr = (float)(-1.3862943611198906 * (v2 * sc) * (v2 * sc));     // -2 ln u = (-2 ln 2) log2 u
+    q.dk = (float)(d2 * sc);
+    q.inv = (float)ldexp(1.0, -q.k);
+    q.S0 = (float)g.S0;
+    q.k0 = (uint32_t)seed;
+    q.k1 = (uint32_t)(seed >> 32);
+    return q;
+}
+
+int philox_rounds() {
+    static const int rounds = [] {
+        const char* e = getenv("AMC_PHILOX_ROUNDS");
+        return (e && atoi(e) == 7) ? 7 : 10;
+    }();
+    return rounds;
+}
+
+// S == nullptr with L_out != nullptr: path-free mode (only the terminal log-prices are stored)
+cudaError_t launch_generate_philox(int dtype, void* S, int32_t* L_out, int64_t ld, int n_steps, int64_t n_local,
+                                   int64_t path_offset, GbmParams g, uint64_t seed, int sm_count, cudaStream_t s) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const int64_t n_vec = dtype == 1 ? (n_local + 3) / 4 : (n_local + 1) / 2;
+    const int64_t n_vec = dtype == 1 ? ((path_offset + n_local + 3) / 4 - path_offset / 4) : (n_local + 1) / 2;
     int64_t blocks = (n_vec + 255) / 256;
     const int64_t cap = (int64_t)sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (dtype == 1)
-        philox_paths_f32_kernel<<<(int)blocks, 256, 0, s>>>((float*)S, ld, n_steps, n_local, path_offset, g, k0, k1);
-    else
-        philox_paths_f64_kernel<<<(int)blocks, 256, 0, s>>>((double*)S, ld, n_steps, n_local, path_offset, g, k0, k1);
+    const int b = (int)blocks;
+    if (dtype == 1) {
+        const QuadGen q = make_quad_gen(g, n_steps, seed);
+        const bool aligned = (path_offset & 3) == 0;
+        const bool seven = philox_rounds() == 7;
+        float* Sf = (float*)S;
+        if (aligned && !seven) philox_quads_f32_kernel<10, true><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else if (aligned) philox_quads_f32_kernel<7, true><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else if (!seven) philox_quads_f32_kernel<10, false><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else philox_quads_f32_kernel<7, false><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+    } else {
+        if (L_out || !S) return cudaErrorInvalidValue;
+        philox_paths_f64_kernel<<<b, 256, 0, s>>>((double*)S, ld, n_steps, n_local, path_offset, g, k0, k1);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Lean (path-free) sets keep no matrix: reading a column, rows, the knock-in index or each path's price at its own step
+// walks the quads forward again from L_0 = 0 (diagnostics / API parity; the sweep itself walks backward from L_n).
+enum LeanWalk { kLeanColumn = 0, kLeanRows = 1, kLeanFirstHit = 2, kLeanGather = 3 };
+
+template <int ROUNDS, int MODE>
+__global__ void __launch_bounds__(256) lean_walk_kernel(QuadGen g, int64_t quad0, int64_t n_local, int n_steps, int t_stop,
+                                                        int64_t p_lo, int64_t p_hi, double barrier,
+                                                        const int32_t* __restrict__ steps, double* __restrict__ out,
+                                                        int32_t* __restrict__ out_i) {
+    const int64_t q_lo = p_lo >> 2, q_hi = (p_hi + 3) >> 2;
+    for (int64_t v = q_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < q_hi; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t quad = (uint64_t)(quad0 + v);
+        int L[4] = {0, 0, 0, 0};
+        int fh[4] = {n_steps + 1, n_steps + 1, n_steps + 1, n_steps + 1};
+        int want[4] = {0, 0, 0, 0};
+        double got[4] = {(double)g.S0, (double)g.S0, (double)g.S0, (double)g.S0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t pp = 4 * v + i;
+            if (MODE == kLeanFirstHit && (double)g.S0 <= barrier) fh[i] = 0;
+            if (MODE == kLeanGather && pp >= p_lo && pp < p_hi) {
+                int w = steps[pp];
+                want[i] = w < 0 ? 0 : (w > n_steps ? n_steps : w);
+            }
+            if (MODE == kLeanRows && pp >= p_lo && pp < p_hi) out[(pp - p_lo) * (int64_t)(n_steps + 1)] = (double)g.S0;
+        }
+        for (int t = 1; t <= t_stop; ++t) {
+            int q[4];
+            quad_increments<ROUNDS>(g, (uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)t, q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                L[i] += q[i];
+                const int64_t pp = 4 * v + i;
+                if (MODE == kLeanColumn) continue;
+                const double x = (double)price_from_log(g, L[i]);
+                if (MODE == kLeanRows && pp >= p_lo && pp < p_hi) out[(pp - p_lo) * (int64_t)(n_steps + 1) + t] = x;
+                if (MODE == kLeanFirstHit && x <= barrier && fh[i] == n_steps + 1) fh[i] = t;
+                if (MODE == kLeanGather && t == want[i]) got[i] = x;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t pp = 4 * v + i;
+            if (pp < p_lo || pp >= p_hi || pp >= n_local) continue;
+            if (MODE == kLeanColumn) out[pp] = t_stop == 0 ? (double)g.S0 : (double)price_from_log(g, L[i]);
+            if (MODE == kLeanFirstHit) out_i[pp] = fh[i];
+            if (MODE == kLeanGather) out[pp] = got[i];
+        }
+    }
+}
+
+cudaError_t launch_lean_walk(int mode, int rounds, const QuadGen& g, int64_t quad0, int64_t n_local, int n_steps, int t_stop,
+                             int64_t p_lo, int64_t p_hi, double barrier, const int32_t* steps_dev, double* out_dev,
+                             int32_t* out_i_dev, int sm_count, cudaStream_t s) {
+    const int64_t nq = ((p_hi + 3) >> 2) - (p_lo >> 2);
+    int64_t blocks = (nq + 255) / 256;
+    if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    const int b = (int)blocks;
+#define AMC_LEAN_WALK(R, M) \
+    lean_walk_kernel<R, M><<<b, 256, 0, s>>>(g, quad0, n_local, n_steps, t_stop, p_lo, p_hi, barrier, steps_dev, out_dev, out_i_dev)
+    if (rounds == 7) {
+        switch (mode) {
+            case kLeanColumn: AMC_LEAN_WALK(7, kLeanColumn); break;
+            case kLeanRows: AMC_LEAN_WALK(7, kLeanRows); break;
+            case kLeanFirstHit: AMC_LEAN_WALK(7, kLeanFirstHit); break;
+            case kLeanGather: AMC_LEAN_WALK(7, kLeanGather); break;
+            default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (mode) {
+            case kLeanColumn: AMC_LEAN_WALK(10, kLeanColumn); break;
+            case kLeanRows: AMC_LEAN_WALK(10, kLeanRows); break;
+            case kLeanFirstHit: AMC_LEAN_WALK(10, kLeanFirstHit); break;
+            case kLeanGather: AMC_LEAN_WALK(10, kLeanGather); break;
+            default: return cudaErrorInvalidValue;
+        }
+    }
+#undef AMC_LEAN_WALK
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Generator self-tests (amc_selftest_*): the DEVICE build of the integer Philox stage for chosen counters (known-answer
+// vectors must come out bit-exact -- philox.cuh takes a different mulhilo branch under __CUDA_ARCH__), and the
+// distribution of the float Box-Muller normals exactly as the path kernel forms them (MUFU lg2 / sqrt / sin / cos).
+template <int ROUNDS>
+__global__ void philox_kat_kernel(const uint32_t* __restrict__ ctr, uint32_t k0, uint32_t k1, int n, uint32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox4 r = philox4x32<ROUNDS>(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = r.v[j];
+}
+
+cudaError_t launch_philox_kat(int rounds, const uint32_t* ctr_dev, uint32_t k0, uint32_t k1, int n, uint32_t* out_dev,
+                              cudaStream_t s) {
+    const int b = (n + 127) / 128;
+    if (rounds == 10) philox_kat_kernel<10><<<b, 128, 0, s>>>(ctr_dev, k0, k1, n, out_dev);
+    else if (rounds == 7) philox_kat_kernel<7><<<b, 128, 0, s>>>(ctr_dev, k0, k1, n, out_dev);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// standard normals of n_quads x n_steps Philox calls (4 normals each), binned on [lo, hi) into n_bins equal bins plus an
+// underflow (bin 0) and an overflow (bin n_bins + 1) bin; stats[block][6] = count, sum z, z^2, z^3, z^4, max |z|
+constexpr int kNormalBinsMax = 4096;
+template <int ROUNDS>
+__global__ void __launch_bounds__(256) normals_hist_kernel(uint32_t k0, uint32_t k1, int64_t n_quads, int n_steps, int n_bins,
+                                                           float lo, float inv_width, unsigned long long* __restrict__ hist,
+                                                           double* __restrict__ stats) {
+    __shared__ unsigned int sh[kNormalBinsMax + 2];
+    __shared__ double red[8 * 6];
+    for (int i = threadIdx.x; i < n_bins + 2; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    float zmax = 0.f;
+    int since_flush = 0;
+    // block-uniform trip count (the flush below has block-wide barriers)
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_quads; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = base + threadIdx.x;
+        for (int t = 1; t <= n_steps && v < n_quads; ++t) {
+            const Philox4 r = philox4x32<ROUNDS>((uint32_t)v, (uint32_t)((uint64_t)v >> 32), (uint32_t)t, kPhiloxDomainQuad, k0, k1);
+            float z[4];
+            box_muller_pair(r.v[0], r.v[1], -1.3862943611198906f, 0.f, z[0], z[1]);
+            box_muller_pair(r.v[2], r.v[3], -1.3862943611198906f, 0.f, z[2], z[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float b = floorf((z[i] - lo) * inv_width);
+                const int bin = b < 0.f ? 0 : (b >= (float)n_bins ? n_bins + 1 : (int)b + 1);
+                atomicAdd(&sh[bin], 1u);
+                const double zd = (double)z[i], z2 = zd * zd;
+                acc[0] += 1.0; acc[1] += zd; acc[2] += z2; acc[3] += z2 * zd; acc[4] += z2 * z2;
+                zmax = fmaxf(zmax, fabsf(z[i]));
+            }
+        }
+        since_flush += n_steps;
+        if (since_flush >= 2048) {                             // flush long before a 32-bit bin can overflow
+            since_flush = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_bins + 2; i += blockDim.x) {
+                if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+                sh[i] = 0u;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins + 2; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    double all[6] = {acc[0], acc[1], acc[2], acc[3], acc[4], 0.0};
+    // max |z|: shuffle maximum, then one slot per warp
+    for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+    __shared__ float wmax[8];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = zmax;
+    block_reduce_store<6, 256>(all, red, stats + (int64_t)blockIdx.x * 6);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < 8; ++w) m = fmaxf(m, wmax[w]);
+        stats[(int64_t)blockIdx.x * 6 + 5] = (double)m;
+    }
+}
+
+cudaError_t launch_normals_hist(int rounds, uint64_t seed, int64_t n_quads, int n_steps, int n_bins, double lo, double hi,
+                                unsigned long long* hist_dev, double* stats_dev, int grid, cudaStream_t s) {
+    if (n_bins < 1 || n_bins > kNormalBinsMax || !(hi > lo)) return cudaErrorInvalidValue;
+    const float inv_width = (float)((double)n_bins / (hi - lo));
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (rounds == 10) normals_hist_kernel<10><<<grid, 256, 0, s>>>(k0, k1, n_quads, n_steps, n_bins, (float)lo, inv_width, hist_dev, stats_dev);
+    else if (rounds == 7) normals_hist_kernel<7><<<grid, 256, 0, s>>>(k0, k1, n_quads, n_steps, n_bins, (float)lo, inv_width, hist_dev, stats_dev);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

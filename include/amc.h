@@ -73,10 +73,22 @@ int amc_comm_allreduce_host(amc_ctx* ctx, double* buf, int n);
 /* ---- path simulation: replaces generate_asset_paths, amc.py:72-81 -------------------------------------- */
 /* K1: counter-based Philox4x32-10 + Box-Muller, log-space cumulative sum, timestep-major vector stores.
  * `n_paths_local` paths whose GLOBAL ids start at `path_offset` (so the union over ranks does not depend on
- * the number of ranks); `n_paths_global` is the total over all ranks. */
+ * the number of ranks); `n_paths_global` is the total over all ranks.
+ * AMC_F32: one Philox call per quad of adjacent paths and step, log2-prices summed exactly in int32 fixed point
+ * (csrc/gbm_quad.cuh); AMC_F64: 53-bit uniforms, double log-price.  AMC_PHILOX_ROUNDS=7 selects Philox4x32-7 for the
+ * float generator (explicit throughput option; 10 rounds is the default). */
 int amc_paths_generate(amc_ctx* ctx, double S0, double r, double sigma, double T, int n_time_steps,
                        int64_t n_paths_local, int64_t path_offset, int64_t n_paths_global, int dtype,
                        uint64_t seed, amc_paths** out);
+/* Path-free ("lean") variant of amc_paths_generate for float paths: NO path matrix is stored --
+ * only each path's terminal fixed-point log2-price (4 bytes per path instead of 4 (n+1)).  amc_lsm_price regenerates
+ * column t-1 from column t inside the backward sweep (L_{t-1} = L_t - q_t, q_t recomputed from the Philox counter: the
+ * exact reverse of the forward integer sum), so prices and exercise decisions equal those of the stored set with the
+ * same seed.  `path_offset` must be a multiple of 4.  Read-back entry points (amc_paths_column / _rows / ...) work on a
+ * lean set by walking the counters forward again (diagnostics; O(t) per element). */
+int amc_paths_generate_lean(amc_ctx* ctx, double S0, double r, double sigma, double T, int n_time_steps,
+                            int64_t n_paths_local, int64_t path_offset, int64_t n_paths_global, uint64_t seed,
+                            amc_paths** out);
 /* K1z: same arithmetic from caller-supplied standard normals Z[p][j] (row-major [n_paths_local][n_time_steps],
  * exactly what amc.py:74 draws) -- the A/B mode: identical inputs to the reference. */
 int amc_paths_from_normals(amc_ctx* ctx, const double* Z, double S0, double r, double sigma, double T,
@@ -214,6 +226,17 @@ int amc_apply_exercise(amc_ctx* ctx, double* cashflows, int64_t* exercise_times,
 int amc_basis_matrix(amc_ctx* ctx, const double* X, int64_t n, int basis, int degree, double* out);
 /* precompute_barrier_hit_matrix, amc.py:171-176: out is [n_paths][n_time_steps+1] row-major bytes (0/1) */
 int amc_barrier_hit_matrix(amc_ctx* ctx, const amc_paths* paths, double barrier, uint8_t* out);
+
+/* ---- generator self-tests (diagnostics; no reference counterpart: amc.py:74 uses NumPy's host stream) -------------- */
+/* The DEVICE build of Philox4x32-`rounds` (10 or 7) on `n` caller-chosen counters: out[i] = philox(counters[i], key).
+ * The Random123 known-answer vectors must come out bit-exact (tests/test_gpu_generator.py). */
+int amc_selftest_philox(amc_ctx* ctx, int rounds, const uint32_t* counters, const uint32_t key[2], int n, uint32_t* out);
+/* Histogram of the float generator's standard normals, formed exactly as the path kernel forms them (Philox quad
+ * counters (quad, step), Box-Muller on the MUFU approximations): 4 * n_quads * n_steps samples binned on [lo, hi) into
+ * n_bins (<= 4096) equal bins; hist[0] / hist[n_bins+1] = under / overflow.  stats = count, sum z, sum z^2, sum z^3,
+ * sum z^4, max |z|. */
+int amc_selftest_normals(amc_ctx* ctx, int rounds, uint64_t seed, int64_t n_quads, int n_steps, int n_bins, double lo,
+                         double hi, uint64_t* hist, double stats[6]);
 
 #ifdef __cplusplus
 }

@@ -47,10 +47,11 @@ UT = dict(S0=100, K=100, r=0.01, sigma=0.2, T=1.0)            # unit_test.py:45
 
 
 def case(name, mkt, n, P, option_type, exercise_type, barrier, basis, degree, kwargs=None,
-         seed=42, steps_detail=False, source=""):
+         seed=42, steps_detail=False, source="", round_paths_f32=False):
     return dict(name=name, **mkt, n_time_steps=n, n_paths=P, option_type=option_type,
                 exercise_type=exercise_type, barrier_level=barrier, basis_type=basis, degree=degree,
-                kwargs=kwargs or {}, seed=seed, steps_detail=steps_detail, source=source)
+                kwargs=kwargs or {}, seed=seed, steps_detail=steps_detail, source=source,
+                round_paths_f32=round_paths_f32)
 
 
 CASES = []
@@ -107,6 +108,17 @@ BIG = [
          dict(scaling=True, scaling_factor=2), steps_detail=True,
          source="BASELINE.json configs[4] at 500k paths, the reference-comparable basis (SURVEY.md 8c: 4.4890595342)"),
 ]
+# The same two runs with the reference fed its own paths ROUNDED TO FLOAT32 (and widened back): what "FP32 path
+# storage" means as an input to the unmodified reference.  The CUDA path with float storage must reproduce THESE to the
+# FP64 bar (same arithmetic, same inputs); their distance from the unrounded runs is the reference's own sensitivity to
+# a 6e-8 relative perturbation of its inputs (exercise decisions are discontinuous in the paths).
+BIG += [
+    case("c3_reduced_f32paths", LS, 252, 1_000_000, "Put", "American", None, "Power", 3, steps_detail=True,
+         source="c3_reduced with paths.astype(float32).astype(float64)", round_paths_f32=True),
+    case("c5_reduced_f32paths", LS, 100, 500_000, "Put", "American", None, "Legendre", 8,
+         dict(scaling=True, scaling_factor=2), steps_detail=True,
+         source="c5_reduced with paths.astype(float32).astype(float64)", round_paths_f32=True),
+]
 BIG_EXPECT = {"c3_reduced": "4.4847469992", "c5_reduced": "4.4890595342"}
 
 
@@ -136,6 +148,8 @@ def run_case(c, check_oracle=True, keep_tau=None):
     dt = c["T"] / c["n_time_steps"]
     np.random.seed(c["seed"])
     paths = ref.generate_asset_paths(*mk)
+    if c.get("round_paths_f32"):
+        paths = paths.astype(np.float32).astype(np.float64)
     with LstsqTap() as tap:
         price, cont = ref.lsmc_option_pricing(paths, c["K"], c["r"], dt, c["option_type"], c["barrier_level"],
                                               c["exercise_type"], c["basis_type"], c["degree"], **c["kwargs"])
@@ -151,6 +165,8 @@ def run_case(c, check_oracle=True, keep_tau=None):
     if check_oracle:
         np.random.seed(c["seed"])
         o_paths = orc.generate_asset_paths(*mk)
+        if c.get("round_paths_f32"):
+            o_paths = o_paths.astype(np.float32).astype(np.float64)
         assert np.array_equal(o_paths, paths), c["name"]
         o = orc.lsm_backward(o_paths, c["K"], c["r"], dt, c["option_type"], c["barrier_level"], c["exercise_type"],
                              c["basis_type"], c["degree"], keep_diag=True, **c["kwargs"])
@@ -198,6 +214,7 @@ def main():
     ap.add_argument("--with-c2", action="store_true")
     ap.add_argument("--with-big", action="store_true")
     ap.add_argument("--only-big", action="store_true", help="carry every other case over from the existing file")
+    ap.add_argument("--big-names", default="", help="comma-separated subset of the big cases to (re)run; the others carry over")
     args = ap.parse_args()
     out_path = os.path.join(HERE, "golden.json")
     old = {}
@@ -213,10 +230,15 @@ def main():
     elif C2["name"] in old:
         recs.append(old[C2["name"]])
     if args.with_big:
-        taus = {}
+        npz = os.path.join(HERE, "big_exercise_steps.npz")
+        taus = dict(np.load(npz)) if os.path.exists(npz) else {}
+        only = set(filter(None, args.big_names.split(",")))
         for c in BIG:
-            recs.append(run_case(c, keep_tau=taus))
-        np.savez_compressed(os.path.join(HERE, "big_exercise_steps.npz"), **taus)
+            if only and c["name"] not in only and c["name"] in old and c["name"] in taus:
+                recs.append(old[c["name"]])
+            else:
+                recs.append(run_case(c, keep_tau=taus))
+        np.savez_compressed(npz, **taus)
     else:
         recs += [old[c["name"]] for c in BIG if c["name"] in old]
     meta = dict(numpy=np.__version__, generator="tests/golden/make_golden.py",

