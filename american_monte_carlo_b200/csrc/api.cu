@@ -1084,6 +1084,14 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     if (p->lean && !persistent)
         return fail(AMC_ERR_STATE, "path-free sets need the persistent sweep (peer-memory transport when sharded)");
     bool used_persistent = false;
+    if (exchange && c->transport == 2 && !persistent) {
+        // the chain's solve launches draw their exchange sequence numbers from a device counter: seed it with this rank's
+        // host-side count of exchanges so far -- the same on every rank however an earlier sweep ended
+        if (c->peer_seq > 0xFFF00000u) c->peer_seq = 0;
+        const uint32_t seed = c->peer_seq;                  // pageable source: staged before the call returns
+        CU(cudaMemcpyAsync(c->peer_err + 16, &seed, 4, cudaMemcpyHostToDevice, c->stream));
+        c->peer_seq += (uint32_t)(regress ? n + 1 : 1);
+    }
     if (persistent) {
         used_persistent = true;
         const int n_passes = regress ? n + 1 : 1;

@@ -45,7 +45,21 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
     }
     pdl_launch_dependents();
     pdl_wait();
-    solve_block<K>(a, a_in, 0u, nullptr);
+    // multi-GPU: every exchange takes the next sequence number from a device counter (never 0), so the launch arguments of
+    // a sweep stay constant from call to call (CUDA-graph replay); the host re-seeds the counter at the start of every
+    // sharded sweep (api.cu), which keeps the ranks in lockstep whatever happened to an earlier sweep
+    uint32_t seq = 0u;
+    if (a.peer.world > 1) {
+        __shared__ uint32_t s_seq;
+        if (threadIdx.x == 0) {
+            uint32_t v = atomicAdd(a.peer.seq_ctr, 1u) + 1u;
+            if (v == 0u) v = atomicAdd(a.peer.seq_ctr, 1u) + 1u;
+            s_seq = v;
+        }
+        __syncthreads();
+        seq = s_seq;
+    }
+    solve_block<K>(a, a_in, seq, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -97,7 +97,12 @@ struct SweepStage {
 // 1), 3 up to degree 5, else 2; double columns 2 (their 96 KB ring allows no more).
 template <typename XT, int D, bool LEAN>
 struct SweepMinBlocks {
-    static constexpr int value = (sizeof(XT) == 4 && !LEAN) ? (D <= 3 ? 4 : (D <= 5 ? 3 : 2)) : 2;
+#ifdef AMC_LEAN_BLOCKS
+    static constexpr int kLean = (D <= 3) ? AMC_LEAN_BLOCKS : 2;
+#else
+    static constexpr int kLean = 2;
+#endif
+    static constexpr int value = LEAN ? kLean : (sizeof(XT) == 4 ? (D <= 3 ? 4 : (D <= 5 ? 3 : 2)) : 2);
 };
 
 // Geometry of one block's share of the sweep and thread 0's copy engine driver (all trivially inlined).

@@ -28,8 +28,11 @@ namespace amc {
 // instructions, 3 MUFU ops.
 //   S == nullptr: nothing is stored per step (path-free mode, amc_paths_generate_lean): only the terminal log-prices
 //   L_n go to `L_out` -- the backward sweep regenerates every earlier column from them.
-template <int ROUNDS, bool ALIGNED>
-__global__ void __launch_bounds__(256) philox_quads_f32_kernel(float* __restrict__ S, int32_t* __restrict__ L_out,
+// MINB = 6: no register cap -- the natural allocation (34 registers, no spills) already gives 6 resident blocks per SM;
+// MINB = 8 caps at 32 registers (a few spills) for 8 blocks.  The launcher sizes the grid as ONE resident wave of MINB
+// blocks per SM.
+template <int ROUNDS, bool ALIGNED, int MINB>
+__global__ void __launch_bounds__(256, (MINB == 8 ? 8 : 1)) philox_quads_f32_kernel(float* __restrict__ S, int32_t* __restrict__ L_out,
                                                                int64_t ld, int n_steps, int64_t n_local,
                                                                int64_t path_offset, QuadGen g) {
     const int64_t quad0 = path_offset >> 2;                        // first global quad that holds a local path
@@ -149,9 +152,17 @@ cudaError_t launch_generate_philox(int dtype, void* S, int32_t* L_out, int64_t l
                                    int64_t path_offset, GbmParams g, uint64_t seed, int sm_count, cudaStream_t s) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int64_t n_vec = dtype == 1 ? ((path_offset + n_local + 3) / 4 - path_offset / 4) : (n_local + 1) / 2;
+    // ONE wave of resident blocks (a second, partial wave would run at a fraction of the occupancy for as long as the
+    // first: ncu r2f_k1 showed 56 % warps active with the grid capped at 8 blocks per SM while only 6 were resident),
+    // and the same number of grid-stride iterations for every thread
+    static const int k1_blocks = (getenv("AMC_K1_BLOCKS") && atoi(getenv("AMC_K1_BLOCKS")) == 8) ? 8 : 6;
+    const int per_sm = dtype == 1 ? (((path_offset & 3) == 0) ? k1_blocks : 6) : 4;              // __launch_bounds__(256, MINB) / the f64 kernel's registers
+    const int64_t cap = (int64_t)sm_count * per_sm;
     int64_t blocks = (n_vec + 255) / 256;
-    const int64_t cap = (int64_t)sm_count * 8;
-    if (blocks > cap) blocks = cap;
+    if (blocks > cap) {
+        const int64_t iters = (n_vec + cap * 256 - 1) / (cap * 256);
+        blocks = (n_vec + 256 * iters - 1) / (256 * iters);
+    }
     if (blocks < 1) blocks = 1;
     const int b = (int)blocks;
     if (dtype == 1) {
@@ -159,10 +170,12 @@ cudaError_t launch_generate_philox(int dtype, void* S, int32_t* L_out, int64_t l
         const bool aligned = (path_offset & 3) == 0;
         const bool seven = philox_rounds() == 7;
         float* Sf = (float*)S;
-        if (aligned && !seven) philox_quads_f32_kernel<10, true><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
-        else if (aligned) philox_quads_f32_kernel<7, true><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
-        else if (!seven) philox_quads_f32_kernel<10, false><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
-        else philox_quads_f32_kernel<7, false><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        if (aligned && !seven && k1_blocks == 8) philox_quads_f32_kernel<10, true, 8><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else if (aligned && !seven) philox_quads_f32_kernel<10, true, 6><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else if (aligned && k1_blocks == 8) philox_quads_f32_kernel<7, true, 8><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else if (aligned) philox_quads_f32_kernel<7, true, 6><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else if (!seven) philox_quads_f32_kernel<10, false, 6><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
+        else philox_quads_f32_kernel<7, false, 6><<<b, 256, 0, s>>>(Sf, L_out, ld, n_steps, n_local, path_offset, q);
     } else {
         if (L_out || !S) return cudaErrorInvalidValue;
         philox_paths_f64_kernel<<<b, 256, 0, s>>>((double*)S, ld, n_steps, n_local, path_offset, g, k0, k1);

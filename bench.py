@@ -572,6 +572,8 @@ def main():
     ap.add_argument("--state", default=None, choices=["float64", "float32"],
                     help="storage of the per-path state (default: float64 for FP64 workloads, float32 for FP32-path ones)")
     ap.add_argument("--lean", action="store_true", help="Philox workloads: path-free set (store_paths=False)")
+    ap.add_argument("--scaling", action="store_true",
+                    help="regress on the standardised column (regression_estimate(scaling=True, scaling_factor=2))")
     ap.add_argument("--no-c3", action="store_true", help="default workload only: skip the north_star_c3 block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -579,6 +581,8 @@ def main():
     if args.paths:
         wl["P"] = args.paths
     wl["state"] = args.state or wl.get("state", "float64")
+    if args.scaling:
+        wl["kw"] = dict(scaling=True, scaling_factor=2)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

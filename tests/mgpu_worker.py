@@ -91,6 +91,12 @@ def main():
     rh = amc.lsm_price(dh, K, r, T / n, "Put", None, "American", "Power", 3, ctx=ctx)
     out["adopted"] = dict(price=float(rh.price), mu_err=float(np.max(np.abs(mu - paths.mean(axis=0)) / mu)),
                           sg_err=float(np.max(np.abs(sg[1:] - paths.std(axis=0)[1:]) / sg[1:])))
+    # (2c) path-free sets shard like stored ones: the persistent sweep kernel exchanges the sums from inside (peer memory)
+    if ctx.transport == "p2p":
+        dl = amc.generate_asset_paths(S0, r, sigma, T, n, Pp, rng="philox", seed=11, dtype="float32", store_paths=False, ctx=ctx)
+        rl = amc.lsm_price(dl, K, r, T / n, "Put", None, "American", "Power", 3, ctx=ctx)
+        dl.free()
+        out["lean"] = dict(multi=float(rl.price), stored_multi=float(rq.price))
     # (4) a host ndarray handed to the reference-shaped entry point under a multi-rank default context is a rank-LOCAL
     # path set (n_global == n_local): no exchange, every rank prices all of it by itself and gets the oracle's price
     small = np.ascontiguousarray(paths[:20_000])
