@@ -720,7 +720,9 @@ extern "C" int amc_paths_from_host(amc_ctx* c, const double* S, int n_time_steps
         });
         if (rc) { amc_paths_free(p); return rc; }
     }
-    rc = measured_maps(c, p);
+    // column statistics are merged over the ranks only where the path axis is sharded over them: a rank-local matrix
+    // (n_global == n_local) involves no collective at all
+    rc = measured_maps(c, p, n_paths_global != n_paths_local);
     if (rc) { amc_paths_free(p); return rc; }
     *out = p;
     return AMC_OK;

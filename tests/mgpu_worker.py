@@ -19,7 +19,7 @@ def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     import datetime
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=60))
     rank, world = dist.get_rank(), dist.get_world_size()
     ctx = init_distributed()
     out = {"transport": ctx.transport}
