@@ -214,15 +214,17 @@ def generate_asset_paths(S0, r, sigma, T, n_time_steps, n_paths, *, rng="numpy",
                  store_paths=False (float32 only) keeps NO path matrix: 4 bytes per path instead of 4 (n+1); the backward
                  sweep regenerates the columns from the counters and takes the same decisions as the stored set.
     """
-    ctx = ctx or default_context()
     n_time_steps, n_paths = int(n_time_steps), int(n_paths)
     did = _dtype_id(dtype)
+    if not store_paths and (rng != "philox" or did != N.F32):
+        raise ValueError("store_paths=False needs rng='philox' and dtype='float32' (the columns are regenerated from "
+                         "the Philox counters of the float generator)")
+    if rng not in ("numpy", "philox"):
+        raise ValueError(f"unknown rng {rng!r}: use 'numpy' or 'philox'")
+    ctx = ctx or default_context()
     lo, hi = shard_range(n_paths, ctx.world_size, ctx.rank, 4 if (rng == "philox" and did == N.F32) else 1)
     h = C.c_void_p()
     if not store_paths:
-        if rng != "philox" or did != N.F32:
-            raise ValueError("store_paths=False needs rng='philox' and dtype='float32' (the columns are regenerated from "
-                             "the Philox counters of the float generator)")
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 62))
         N.check(N.lib().amc_paths_generate_lean(ctx.handle, float(S0), float(r), float(sigma), float(T), n_time_steps,

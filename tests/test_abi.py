@@ -69,6 +69,26 @@ def test_shard_range_partitions_the_path_axis():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_range_in_quads_for_the_float_generator():
+    """unit=4: every shard starts on a quad boundary (one Philox call of the float generator serves four adjacent paths;
+    the path-free mode requires it), sizes differ by at most one quad, the union is the whole range."""
+    from american_monte_carlo_b200 import shard_range
+    for P, W in [(100_000_000, 8), (1_000_003, 2), (1_000_003, 3), (5, 4), (0, 2), (4, 8)]:
+        parts = [shard_range(P, W, r, 4) for r in range(W)]
+        assert parts[0][0] == 0 and parts[-1][1] == P
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(lo % 4 == 0 for lo, hi in parts if hi > lo)
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 7                     # one quad, plus the ragged tail of the last shard
+
+
+def test_path_free_mode_rejects_what_it_cannot_regenerate():
+    import american_monte_carlo_b200 as pkg
+    for kw in (dict(rng="numpy", dtype="float32"), dict(rng="philox", dtype="float64")):
+        with pytest.raises(ValueError, match="store_paths=False"):
+            pkg.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 10, 100, store_paths=False, **kw)
+
+
 def test_c_example_builds_against_the_header_and_fails_loudly_without_a_gpu(libamc_path, tmp_path):
     """examples/price_put.c is a plain-C host of include/amc.h: it must compile and link against libamc.so; run without
     a CUDA device it must stop at amc_ctx_create with the library's message (no CPU path), with one it prices."""
