@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) lsm_solve_kernel(const Solve
         __syncthreads();
         seq = s_seq;
     }
-    solve_block<K>(a, a_in, seq, nullptr);
+    solve_block<K, false>(a, a_in, seq, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -39,6 +39,29 @@ __device__ __noinline__ void solve_scalar_outofline(const SolveArgs& a, const do
 }
 
 template <int K>
+__device__ __forceinline__ void solve_scalar_inline(const SolveArgs& a, const double* part0) {
+    constexpr int d = K - 1;
+    double h[2 * d + 1], g[K];
+    h[0] = a.spec.n_paths;
+#pragma unroll
+    for (int m = 1; m <= 2 * d; ++m) h[m] = part0[m - 1];
+#pragma unroll
+    for (int m = 0; m <= d; ++m) g[m] = part0[2 * d + m];
+    SolveResult res;
+    lsm_solve_t<K>(a.spec, h, g, a.y_scale, a.mu_ref, a.sigma_ref, &res);
+#pragma unroll
+    for (int i = 0; i < kMaxK; ++i) {
+        a.gamma[i] = res.gamma[i];
+        if (a.beta) a.beta[i] = res.beta[i];
+        if (a.sv) a.sv[i] = res.sv[i];
+    }
+    if (a.mean_std) { a.mean_std[0] = res.mean_x; a.mean_std[1] = res.std_x; a.mean_std[2] = res.pivot_loss; }
+    if (a.rank) a.rank[0] = res.rank;
+}
+
+// OUT_OF_LINE: the scalar routine as a call (persistent sweep kernel) or inlined with its matrices in registers (the
+// dedicated solve kernel, which has a block to itself)
+template <int K, bool OUT_OF_LINE>
 __device__ __forceinline__ void solve_block(const SolveArgs& a, const SolveArgs& a_in, uint32_t seq, uint32_t* sync) {
     constexpr int d = K - 1;
     constexpr int nacc = 3 * d + 1;
@@ -127,7 +150,10 @@ __device__ __forceinline__ void solve_block(const SolveArgs& a, const SolveArgs&
         // truncation, SVD diagnostics) falls through to the scalar routine on thread 0
         const bool solved = lsm_solve_warp<K>(a.spec, &part[0][0], &part[0][2 * d], a.y_scale, a.mu_ref, a.sigma_ref, solve_sh,
                                               a.gamma, a.beta, a.sv, a.mean_std, a.rank);
-        if (!solved && threadIdx.x == 0) solve_scalar_outofline<K>(a, &part[0][0]);
+        if (!solved && threadIdx.x == 0) {
+            if (OUT_OF_LINE) solve_scalar_outofline<K>(a, &part[0][0]);
+            else solve_scalar_inline<K>(a, &part[0][0]);
+        }
     }
     __syncthreads();
 }

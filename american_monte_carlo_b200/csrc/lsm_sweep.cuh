@@ -77,7 +77,7 @@ __device__ __noinline__ void sweep_solve_pass(const SweepArgs& a, int p, int t) 
     sv.mean_std = a.solve.mean_std ? a.solve.mean_std + (size_t)row * 3 : nullptr;
     sv.rank = a.solve.rank ? a.solve.rank + row : nullptr;
     const uint32_t seq = (a.solve.peer.world > 1) ? a.seq_base + (uint32_t)p + 1u : 0u;
-    solve_block<K>(sv, sv, seq, a.sync);
+    solve_block<K, true>(sv, sv, seq, a.sync);
     if (threadIdx.x == 0) {
         __threadfence();
         st_release_u32(a.sync + kSyncPublished, (uint32_t)p + 1u);
