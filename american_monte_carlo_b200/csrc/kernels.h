@@ -65,9 +65,11 @@ constexpr int kPeerRing = 4;
 struct PeerArgs {
     uint4* mailbox[kPeerMax] = {};  // mailbox[q] = rank q's mailbox mapped into this process (cudaIpc); [rank] = own
     int world = 0, rank = 0;        // world <= 1: no exchange
-    uint32_t* seq_ctr = nullptr;    // device counter: every all-reduce takes the next sequence number (never 0); all
-                                    // ranks run the same chain of solve launches, so the numbers agree -- and the launch
-                                    // arguments stay constant from sweep to sweep (CUDA-graph replay)
+    uint32_t* seq_ctr = nullptr;    // launch chain: device counter from which every solve launch takes the next sequence
+                                    // number (never 0), so the launch arguments stay constant from sweep to sweep
+                                    // (CUDA-graph replay); the host re-seeds it at the start of every sharded sweep with
+                                    // its own count of exchanges, which keeps the ranks in lockstep whatever happened to
+                                    // an earlier sweep.  The persistent kernel gets its numbers as SweepArgs::seq_base.
     int* err = nullptr;             // device flag: set to 1 if a peer did not show up in time
 };
 

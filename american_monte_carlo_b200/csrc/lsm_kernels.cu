@@ -188,7 +188,7 @@ static inline int blocks_for(int64_t n, int threads, int cap) {
 
 cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const double* gamma_dev, int degree, double mu,
                                 double isg, int clamp, double* out_dev, cudaStream_t s) {
-    const int grid = blocks_for(n, 256, 148 * 8);
+    const int grid = blocks_for(n, 256, device_sm_count() * 8);
     if (dtype == 1)
         continuation_kernel<float><<<grid, 256, 0, s>>>((const float*)x, n, gamma_dev, degree, mu, isg, clamp, out_dev);
     else
@@ -198,24 +198,24 @@ cudaError_t launch_continuation(int dtype, const void* x, int64_t n, const doubl
 
 cudaError_t launch_discount(const double* cf_dev, const int64_t* tau_dev, int64_t n, int64_t t, double r, double dt,
                             double* y_dev, cudaStream_t s) {
-    discount_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, s>>>(cf_dev, tau_dev, n, t, r, dt, y_dev);
+    discount_kernel<<<blocks_for(n, 256, device_sm_count() * 8), 256, 0, s>>>(cf_dev, tau_dev, n, t, r, dt, y_dev);
     return cudaGetLastError();
 }
 
 cudaError_t launch_apply_exercise(double* cf_dev, int64_t* tau_dev, const double* ev_dev, const double* cont_dev,
                                   const int64_t* idx_dev, int64_t m, int64_t t, cudaStream_t s) {
-    apply_exercise_kernel<<<blocks_for(m, 256, 148 * 8), 256, 0, s>>>(cf_dev, tau_dev, ev_dev, cont_dev, idx_dev, m, t);
+    apply_exercise_kernel<<<blocks_for(m, 256, device_sm_count() * 8), 256, 0, s>>>(cf_dev, tau_dev, ev_dev, cont_dev, idx_dev, m, t);
     return cudaGetLastError();
 }
 
 cudaError_t launch_intrinsic(const double* S_dev, int64_t n, double K, int is_put, double* out_dev, cudaStream_t s) {
-    intrinsic_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, s>>>(S_dev, n, K, is_put, out_dev);
+    intrinsic_kernel<<<blocks_for(n, 256, device_sm_count() * 8), 256, 0, s>>>(S_dev, n, K, is_put, out_dev);
     return cudaGetLastError();
 }
 
 cudaError_t launch_basis_matrix(const double* X_dev, int64_t n, int basis, int degree, double* out_dev,
                                 cudaStream_t s) {
-    basis_matrix_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, s>>>(X_dev, n, basis, degree, out_dev);
+    basis_matrix_kernel<<<blocks_for(n, 256, device_sm_count() * 8), 256, 0, s>>>(X_dev, n, basis, degree, out_dev);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "gbm_quad.cuh"
 #include "philox.cuh"
 
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kZPaths) normals_paths_kernel(const double* __
 cudaError_t launch_from_normals(int dtype, const double* Z_dev, void* S, int64_t ld, int n_steps, int64_t n_local,
                                 GbmParams g, cudaStream_t s) {
     int64_t blocks = (n_local + kZPaths - 1) / kZPaths;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > device_sm_count() * 32) blocks = device_sm_count() * 32;
     if (blocks < 1) blocks = 1;
     const bool wide = (n_steps % 2 == 0) && (((uintptr_t)Z_dev & 15) == 0);
     const int b = (int)blocks;
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const double* __restr
 cudaError_t launch_transpose_in(int dtype, const double* in, void* S, int64_t ld, int n_cols, int64_t n_local,
                                 cudaStream_t s) {
     int64_t tiles = ((n_local + 31) / 32) * ((n_cols + 31) / 32);
-    if (tiles > 148 * 32) tiles = 148 * 32;
+    if (tiles > device_sm_count() * 32) tiles = device_sm_count() * 32;
     if (tiles < 1) tiles = 1;
     if (dtype == 1)
         transpose_in_kernel<float><<<(int)tiles, 256, 0, s>>>(in, (float*)S, ld, n_cols, n_local);
@@ -505,7 +506,7 @@ cudaError_t launch_gather_rows(int dtype, const void* S, int64_t ld, int n_cols,
                                double* out_dev, cudaStream_t s) {
     int64_t total = (p1 - p0) * n_cols;
     int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     if (dtype == 1)
         gather_rows_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)S, ld, n_cols, p0, p1, out_dev);
@@ -528,7 +529,7 @@ __global__ void gather_steps_kernel(const XT* __restrict__ S, int64_t ld, int n_
 cudaError_t launch_gather_steps(int dtype, const void* S, int64_t ld, int n_cols, int64_t n, const int32_t* steps_dev,
                                 double* out_dev, cudaStream_t s) {
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     if (dtype == 1)
         gather_steps_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)S, ld, n_cols, n, steps_dev, out_dev);
@@ -545,7 +546,7 @@ __global__ void column_to_f64_kernel(const XT* __restrict__ col, int64_t n, doub
 
 cudaError_t launch_column_to_f64(int dtype, const void* col, int64_t n, double* out_dev, cudaStream_t s) {
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     if (dtype == 1)
         column_to_f64_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)col, n, out_dev);
@@ -609,7 +610,7 @@ __global__ void first_hit_kernel(const XT* __restrict__ S, int64_t ld, int n_col
 cudaError_t launch_first_hit(int dtype, const void* S, int64_t ld, int n_cols, int64_t n_local, double barrier,
                              int32_t* first_hit_dev, cudaStream_t s) {
     int64_t blocks = (n_local + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
     if (blocks < 1) blocks = 1;
     if (dtype == 1)
         first_hit_kernel<float><<<(int)blocks, 256, 0, s>>>((const float*)S, ld, n_cols, n_local, barrier, first_hit_dev);
@@ -632,7 +633,7 @@ cudaError_t launch_hit_matrix(const int32_t* first_hit_dev, int n_cols, int64_t 
                               cudaStream_t s) {
     int64_t total = n_local * n_cols;
     int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     hit_matrix_kernel<<<(int)blocks, 256, 0, s>>>(first_hit_dev, n_cols, n_local, out_dev);
     return cudaGetLastError();

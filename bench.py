@@ -418,7 +418,10 @@ def measure(rt, name, wl, steps, warmup, lean=False, want_e2e=True, sampler=None
         price=price)
     tr = measured_traffic(name)
     if tr and tr.get("paths_per_gpu") == P_local and not lean:
-        out["roofline"]["traffic"] = tr.get("dram_bytes_per_sweep")
+        # per launch, like `achieved`: the chain launches once per time step, the persistent kernel once per sweep
+        out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch") if launches > 1 else tr.get("dram_bytes_per_sweep")
+        out["roofline"]["traffic_frac_of_peak"] = (tr.get("dram_bytes_per_launch") / (step_ms / launches * 1e-3) / 1e9 / peak
+                                                   if launches > 1 else None)
         out["roofline"]["traffic_source"] = tr.get("source")
     del Z_host, Z_dev
     return out

@@ -45,6 +45,24 @@ def main():
             dh = amc.paths_from_host(host, dtype=dtype)
             amc.lsm_price(dh, K, r, T / n, "Put", None, "American", "Power", 2)
             dh.free()
+        # path-free set: the cooperative sweep kernel, every mode, against the stored set of the same seed
+        ds = amc.generate_asset_paths(S0, r, sigma, T, n, P, rng="philox", seed=5, dtype="float32")
+        dl = amc.generate_asset_paths(S0, r, sigma, T, n, P, rng="philox", seed=5, dtype="float32", store_paths=False)
+        for kw in (dict(), dict(state_dtype="float32"), dict(scaling=True)):
+            for barrier in (None, 33.0):
+                for ex_type in ("American", "European"):
+                    for basis, deg in (("Power", 3), ("Legendre", 8), ("Power", 0)):
+                        a = amc.lsm_price(ds, K, r, T / n, "Put", barrier, ex_type, basis, deg, want_exercise_steps=True,
+                                          want_regression=True, **kw)
+                        b = amc.lsm_price(dl, K, r, T / n, "Put", barrier, ex_type, basis, deg, want_exercise_steps=True,
+                                          want_regression=True, **kw)
+                        assert np.isfinite(b.price) and abs(a.price - b.price) <= 1e-10 * max(abs(a.price), 1e-12)
+                        assert (a.exercise_steps == b.exercise_steps).all()
+        assert np.array_equal(np.asarray(dl), np.asarray(ds))
+        _, cont = amc.lsmc_option_pricing(dl, K, r, T / n, "Put", None, "American", "Chebyshev", 4)
+        assert len(amc.compute_ccr_exposures(cont)) == n + 1
+        ds.free()
+        dl.free()
     x = np.linspace(30, 50, 1001)
     amc.intrinsic_value(x, 40.0, "Put")
     amc.get_basis_polynomials(x, "Legendre", 5)
