@@ -49,6 +49,14 @@ int main(void) {
     CHECK(amc_lsm_price_batch(ctx, paths, ladder, NK, prices, NULL, NULL, 0));
     for (int i = 0; i < NK; ++i) printf("  K=%.0f  %.5f\n", ladder[i].K, prices[i]);
 
+    /* the same contract on a path-free set: no path matrix (4 bytes per path instead of 4 (n+1)), same price */
+    amc_paths* lean = NULL;
+    double lean_price = 0.0;
+    CHECK(amc_paths_generate_lean(ctx, S0, r, sigma, T, n, P, 0, P, 42u, &lean));
+    CHECK(amc_lsm_price(ctx, lean, &spec, &lean_price, NULL, NULL, NULL, NULL, 0));
+    printf("path-free set: %.5f (difference %.1e)\n", lean_price, lean_price - price);
+    CHECK(amc_paths_free(lean));
+
     CHECK(amc_paths_free(paths));
     CHECK(amc_ctx_destroy(ctx));
     return 0;

@@ -108,3 +108,5 @@ def test_plain_c_host_prices_through_the_abi(libamc_path, tmp_path):
     ladder = [float(l.split()[1]) for l in lines[1:6]]
     assert len(ladder) == 5 and all(b > a for a, b in zip(ladder, ladder[1:]))     # put price increases with the strike
     assert abs(ladder[2] - price) <= 1e-9 * price                      # K = 40 inside the batch == the single contract
+    lean = float(lines[6].split(":")[1].split()[0])                    # path-free set of the same seed: the same price
+    assert lines[6].startswith("path-free set") and abs(lean - price) <= 2e-5 * price   # printed to 5 decimals
