@@ -42,7 +42,7 @@ def main():
                             "lsm_sweep_kernel<double, double, 3, false>", "lsm_step_tma_kernel<float, float, 3>",
                             "lsm_step_tma_kernel<float, double, 3>", "lsm_step_tma_kernel<double, double, 3>",
                             "lsm_step_tma_kernel<float, float, 8>", "lsm_solve_kernel<4>", "lsm_solve_kernel<9>",
-                            "philox_quads_f32_kernel<10, true>", "philox_quads_f32_kernel<7, true>", "philox_paths_f64_kernel",
+                            "philox_quads_f32_kernel<10, true, 6>", "philox_quads_f32_kernel<7, true, 6>", "philox_paths_f64_kernel",
                             "normals_paths_kernel<double, true>", "normals_paths_kernel<float, true>", "sel_hist_kernel",
                             "first_hit_kernel<float>", "lean_walk_kernel<10, 0>"]
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)}: static instruction counts per kernel (sm_100a)")
