@@ -88,3 +88,37 @@ def test_float_path_storage_is_exact_on_its_own_inputs(amc, basis, degree, kw):
     assert abs(f32.price - want.price) <= 2e-7 * want.price
     assert (f32.exercise_steps != want.exercise_times).mean() < 1e-4
     dp.free()
+
+
+lean_contract = st.fixed_dictionaries(dict(
+    seed=st.integers(0, 2 ** 40), P=st.integers(60, 9000), n=st.integers(1, 40),
+    S0=st.sampled_from([20.0, 36.0, 100.0]), moneyness=st.floats(0.8, 1.2), r=st.floats(0.0, 0.08),
+    sigma=st.floats(0.0, 0.6), T=st.sampled_from([0.25, 1.0, 3.0]), opt=st.sampled_from(["Put", "Call"]),
+    ex=st.sampled_from(["American", "European"]), barrier=st.sampled_from([None, 0.7, 0.9]),
+    basis=st.sampled_from(["Power", "Chebyshev", "Legendre", "Laguerre"]), degree=st.integers(0, 5), scaling=st.booleans(),
+    state=st.sampled_from(["float64", "float32"])))
+
+
+@settings(max_examples=40, deadline=None, derandomize=True)
+@given(lean_contract)
+def test_random_path_free_sets_price_like_their_stored_twins(c):
+    """Path-free sets (no path matrix; columns regenerated from the Philox counters inside the cooperative sweep kernel)
+    against the stored float set of the same seed, over random markets, shapes and contracts: bit-identical columns,
+    the same exercise step for every path, prices equal to summation-order rounding -- including sigma = 0, where the
+    fixed-point scale of the log-price is set by the drift alone."""
+    amc = _AMC["m"]
+    gen = dict(rng="philox", seed=c["seed"], dtype="float32")
+    stored = amc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], c["n"], c["P"], **gen)
+    lean = amc.generate_asset_paths(c["S0"], c["r"], c["sigma"], c["T"], c["n"], c["P"], store_paths=False, **gen)
+    t = c["n"] // 2
+    assert np.array_equal(lean.column(t), stored.column(t)) and np.array_equal(lean.column(c["n"]), stored.column(c["n"]))
+    K = c["S0"] * c["moneyness"]
+    barrier = None if c["barrier"] is None else c["S0"] * c["barrier"]
+    kw = dict(scaling=True) if c["scaling"] else {}
+    args = (K, c["r"], c["T"] / c["n"], c["opt"], barrier, c["ex"], c["basis"], c["degree"])
+    a = amc.lsm_price(stored, *args, want_exercise_steps=True, state_dtype=c["state"], **kw)
+    b = amc.lsm_price(lean, *args, want_exercise_steps=True, state_dtype=c["state"], **kw)
+    stored.free()
+    lean.free()
+    assert int((a.exercise_steps != b.exercise_steps).sum()) == 0, c
+    assert abs(a.price - b.price) <= 1e-10 * max(abs(a.price), 1e-6), (c, a.price, b.price)
