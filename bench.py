@@ -577,6 +577,8 @@ def main():
     ap.add_argument("--lean", action="store_true", help="Philox workloads: path-free set (store_paths=False)")
     ap.add_argument("--scaling", action="store_true",
                     help="regress on the standardised column (regression_estimate(scaling=True, scaling_factor=2))")
+    ap.add_argument("--degree", type=int, default=None, help="override the basis degree of the workload (experiments)")
+    ap.add_argument("--basis", default=None, help="override the basis family of the workload (experiments)")
     ap.add_argument("--no-c3", action="store_true", help="default workload only: skip the north_star_c3 block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -586,6 +588,10 @@ def main():
     wl["state"] = args.state or wl.get("state", "float64")
     if args.scaling:
         wl["kw"] = dict(scaling=True, scaling_factor=2)
+    if args.degree is not None:
+        wl["degree"] = args.degree
+    if args.basis:
+        wl["basis"] = args.basis
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
