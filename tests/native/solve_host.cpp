@@ -30,3 +30,8 @@ extern "C" void amc_test_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t 
     amc::Philox4 r = amc::philox4x32_10(c0, c1, c2, c3, k0, k1);
     for (int i = 0; i < 4; ++i) out[i] = r.v[i];
 }
+
+#include "../../american_monte_carlo_b200/csrc/gbm_quad.cuh"
+extern "C" int amc_test_fixed_point_bits(double drift_log2, double vol_log2, int n_steps) {
+    return amc::fixed_point_bits(drift_log2, vol_log2, n_steps);
+}

@@ -20,10 +20,11 @@ def host_solver():
     src = os.path.join(HERE, "native", "solve_host.cpp")
     hdr = os.path.join(ROOT, "american_monte_carlo_b200", "csrc", "lsm_solve.h")
     hdr2 = os.path.join(ROOT, "american_monte_carlo_b200", "csrc", "philox.cuh")
+    hdr3 = os.path.join(ROOT, "american_monte_carlo_b200", "csrc", "gbm_quad.cuh")
     out_dir = os.path.join(HERE, "native", "_build")
     so = os.path.join(out_dir, "libamc_solve_host.so")
     os.makedirs(out_dir, exist_ok=True)
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2), os.path.getmtime(hdr3)):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src])
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)

@@ -125,3 +125,36 @@ def test_philox_known_answer_vectors():
     assert [hex(v) for v in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
     lib.amc_test_philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, out)
     assert [hex(v) for v in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_fixed_point_scale_of_the_float_generator():
+    """gbm_quad.cuh::fixed_point_bits (host build): the log2-price of the float generator is an int32 sum of increments in
+    units of 2^-k.  k must keep the largest possible increment (Box-Muller radius <= 6.8) inside the exact range of the
+    magic-number float -> int conversion (2^22) and an 8-sigma excursion of the whole path inside int32, over the whole
+    range of markets and step counts -- including sigma = 0, where only the drift sets the scale."""
+    import ctypes
+    import math
+    lib = emu.host_solver()
+    lib.amc_test_fixed_point_bits.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int]
+    lib.amc_test_fixed_point_bits.restype = ctypes.c_int
+    log2e = 1.4426950408889634
+    seen = set()
+    for sigma in (0.0, 0.01, 0.2, 0.6, 1.5):
+        for T in (0.01, 1.0, 30.0):
+            for n in (1, 4, 50, 252, 5000):
+                for r in (0.0, 0.06, -0.02):
+                    dt = T / n
+                    d2 = (r - 0.5 * sigma * sigma) * dt * log2e
+                    v2 = sigma * math.sqrt(dt) * log2e
+                    k = lib.amc_test_fixed_point_bits(d2, v2, n)
+                    seen.add(k)
+                    assert 4 <= k <= 30
+                    gmax = abs(d2) + v2 * 6.8
+                    span = n * abs(d2) + v2 * (8.0 * math.sqrt(n) + 7.0) + 1.0
+                    if k > 4:                                   # k = 4 is the floor for absurd markets
+                        assert gmax * 2.0 ** k <= 2.0 ** 22 * (1 + 1e-12), (sigma, T, n, r, k)
+                        assert span * 2.0 ** k <= 2.0 ** 30 * (1 + 1e-12), (sigma, T, n, r, k)
+                    # not wastefully small: one more bit would break one of the two bounds (or hit the cap)
+                    assert k == 30 or gmax * 2.0 ** (k + 1) > 2.0 ** 22 or span * 2.0 ** (k + 1) > 2.0 ** 30
+    assert lib.amc_test_fixed_point_bits(0.06 / 252 * log2e - 0.02 / 252 * log2e, 0.2 * math.sqrt(1 / 252) * log2e, 252) == 25
+    assert len(seen) > 5
