@@ -416,3 +416,26 @@ def test_host_arrays_are_streamed_in_chunks_with_identical_results(amc, monkeypa
     np.testing.assert_array_equal(np.asarray(adopted32), A.astype(np.float32).astype(np.float64))
     for d in (one, many, adopted, adopted32):
         d.free()
+
+
+@pytest.mark.parametrize("name", ["small_power8_unscaled", "small_chebyshev10_unscaled", "small_legendre8_scaled",
+                                  "ut_Put_American_None", "ut_Call_American_80", "nb_american_put"])
+def test_rank_truncated_steps_through_the_production_solve(amc, golden, name):
+    """Without want_svd the solve takes its production route: the full-rank certificate, and -- from degree 6 -- the
+    warp-parallel Jacobi SVD for the steps that numpy truncates (degree-8 / degree-10 unscaled bases: every step).  Ranks
+    per step, every exercise decision and the price must be the reference's, and the singular values reported for the
+    truncated steps must be numpy's."""
+    c = golden[name]
+    Z, paths, o = oracle_case(c)
+    dp = amc.paths_from_normals(Z, c["S0"], c["r"], c["sigma"], c["T"])
+    res = amc.lsm_price(dp, *price_args(c), **c["kwargs"], want_exercise_steps=True, want_regression=True)
+    dp.free()
+    n = c["n_time_steps"]
+    assert int((res.exercise_steps != o.exercise_times).sum()) == 0
+    assert res.rank[:n].tolist() == c["ranks"]
+    assert rel(res.price, c["price"]) <= 1e-10
+    for t, rec in c.get("steps", {}).items():
+        t = int(t)
+        r = rec["rank"]
+        if r < c["degree"] + 1 and c["degree"] >= 6 and res.sv[t, 1] > 0:      # truncated step solved by the warp routine
+            np.testing.assert_allclose(res.sv[t, :r], rec["sv"][:r], rtol=1e-6)
