@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libamc.so")
 SOURCES = ["lsm_step_f32.cu", "lsm_step_f64.cu", "lsm_step_f32s.cu", "lsm_sweep_lean.cu", "lsm_kernels.cu", "api.cu", "pathgen.cu", "ccr.cu"]
-HEADERS = ["common.cuh", "gbm_quad.cuh", "kernels.h", "lsm_solve.h", "philox.cuh", "lsm_step.cuh", "lsm_sweep.cuh", "launch.cuh", "lsm_solve_warp.cuh", os.path.join(ROOT, "include", "amc.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "amc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
