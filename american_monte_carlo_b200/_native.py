@@ -30,7 +30,8 @@ class LsmSteps(C.Structure):
 
 class LsmTiming(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("step_kernel_ms", C.c_float), ("solve_kernel_ms", C.c_float),
-                ("step_launches", C.c_int), ("solve_launches", C.c_int), ("other_launches", C.c_int)]
+                ("step_launches", C.c_int), ("solve_launches", C.c_int), ("other_launches", C.c_int),
+                ("sweep_kind", C.c_int)]
 
 
 # name -> (restype, argtypes); the CPU-only test tier checks every symbol of include/amc.h is exported

@@ -339,7 +339,7 @@ def lsm_price(paths, K, r, dt, option_type, barrier_level=None, exercise_type="E
                                       cf.ctypes.data if cf is not None else None, C.byref(timing), int(bool(profile))))
         tm = dict(total_ms=timing.total_ms, step_kernel_ms=timing.step_kernel_ms, solve_kernel_ms=timing.solve_kernel_ms,
                   step_launches=timing.step_launches, solve_launches=timing.solve_launches,
-                  other_launches=timing.other_launches)
+                  other_launches=timing.other_launches, sweep_kind=timing.sweep_kind)
         res = LsmResult(np.float64(price.value), n, int(degree), st, tm, ex, cf)
         worst = float(st["pivot_loss"].max()) if rows else 0.0
         if worst > PIVOT_LOSS_WARN:
@@ -390,7 +390,8 @@ def lsm_price_batch(paths, contracts, r, dt, barrier_level=None, basis_type="Che
                                             int(bool(profile))))
         prices_timing = dict(total_ms=timing.total_ms, step_kernel_ms=timing.step_kernel_ms,
                              solve_kernel_ms=timing.solve_kernel_ms, step_launches=timing.step_launches,
-                             solve_launches=timing.solve_launches, other_launches=timing.other_launches)
+                             solve_launches=timing.solve_launches, other_launches=timing.other_launches,
+                             sweep_kind=timing.sweep_kind)
         lsm_price_batch.last_timing = prices_timing
         return (prices, gamma) if want_gamma else prices
     finally:

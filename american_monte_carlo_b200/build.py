@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libamc.so")
-SOURCES = ["lsm_step_f32.cu", "lsm_step_f64.cu", "lsm_step_f32s.cu", "lsm_sweep_lean.cu", "lsm_kernels.cu", "api.cu", "pathgen.cu", "ccr.cu"]
+SOURCES = ["lsm_step_f32.cu", "lsm_step_f64.cu", "lsm_step_f32s.cu", "lsm_sweep_lean.cu", "lsm_cluster_f32.cu", "lsm_cluster_f64.cu", "lsm_cluster_f32s.cu", "lsm_kernels.cu", "api.cu", "pathgen.cu", "ccr.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join(ROOT, "include", "amc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

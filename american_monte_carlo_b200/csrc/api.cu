@@ -112,6 +112,10 @@ struct amc_ctx {
     DevBuf U, tau, first_hit, partials, sums, diag, stage, misc, batch_tab, ccr, tabs, syncbuf, lstate, regx;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;      // around the persistent sweep kernel
     int sweep_grid_cache[4][AMC_MAX_K];
+    // one-cluster sweep of small path sets (lsm_cluster.cuh): path capacity per storage combination and degree
+    // (-1: not asked yet, 0: unavailable), and the tables last uploaded for it (same contract again -> no copy)
+    int64_t cluster_cap[3][AMC_MAX_K];
+    std::vector<unsigned char> tabs_host;
     uint32_t peer_seq = 0;          // sequence numbers of the peer exchange are handed out per sweep by the host: every
                                     // rank advances by the same amount per sharded sweep, also when a sweep failed
     std::vector<amc_paths*> live_paths;   // path sets not yet freed: invalidated (not leaked, not dangling) on destroy
@@ -228,6 +232,8 @@ extern "C" int amc_ctx_create(int device, void* stream, amc_ctx** out) {
         for (int j = 0; j < AMC_MAX_K; ++j) c->grid_cache[i][j] = 0;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < AMC_MAX_K; ++j) c->sweep_grid_cache[i][j] = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < AMC_MAX_K; ++j) c->cluster_cap[i][j] = -1;
     *out = c;
     return AMC_OK;
 }
@@ -1082,10 +1088,19 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     // on every workload (profiles/r2_persistent_vs_chain.md: the streaming loop needs the whole 64-register budget of 4
     // blocks per SM; sweep-level state and the in-kernel solve spill).  AMC_PERSISTENT=1 selects it for stored sets too.
     static const int opt_persistent = getenv("AMC_PERSISTENT") ? atoi(getenv("AMC_PERSISTENT")) : 0;
-    const bool persistent = C == 1 && (opt_persistent || p->lean) && (!exchange || c->transport == 2);
+    // Small stored sets (everything fits the shared memory of one 16-CTA cluster) are priced by the one-cluster kernel
+    // (lsm_cluster.cuh): ~4 us per step instead of the chain's 6-8.  AMC_CLUSTER=0 keeps them on the chain.
+    static const int opt_cluster = getenv("AMC_CLUSTER") ? atoi(getenv("AMC_CLUSTER")) : 1;
+    bool cluster = false;
+    if (C == 1 && !exchange && !p->lean && !opt_persistent && opt_cluster && P >= 1) {
+        int64_t& cap = c->cluster_cap[sf32 ? 2 : dtype][D];
+        if (cap < 0) cap = cluster_sweep_capacity(dtype, sf32, D);
+        cluster = P <= cap;
+    }
+    const bool persistent = C == 1 && (opt_persistent || p->lean || cluster) && (!exchange || c->transport == 2);
     if (p->lean && !persistent)
         return fail(AMC_ERR_STATE, "path-free sets need the persistent sweep (peer-memory transport when sharded)");
-    bool used_persistent = false;
+    bool used_persistent = false, used_cluster = false, chain_fallback = false;
     if (exchange && c->transport == 2 && !persistent) {
         // the chain's solve launches draw their exchange sequence numbers from a device counter: seed it with this rank's
         // host-side count of exchanges so far -- the same on every rank however an earlier sweep ended
@@ -1095,15 +1110,20 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         c->peer_seq += (uint32_t)(regress ? n + 1 : 1);
     }
     if (persistent) {
-        used_persistent = true;
+        used_persistent = !cluster;
+        used_cluster = cluster;
         const int n_passes = regress ? n + 1 : 1;
         const int lean = p->lean ? 1 : 0;
-        int& gcache = c->sweep_grid_cache[lean ? 3 : (sf32 ? 2 : dtype)][D];
-        if (gcache == 0) gcache = sweep_grid_size(dtype, sf32, D, lean, c->sm_count);
-        int64_t need = (P + 1023) / 1024;
-        if (need < 1) need = 1;
-        const int wgrid = (int)(need < gcache ? need : gcache);
-        if (getenv("AMC_SWEEP_DEBUG")) {
+        int wgrid = 1;
+        if (!cluster) {
+            int& gcache = c->sweep_grid_cache[lean ? 3 : (sf32 ? 2 : dtype)][D];
+            if (gcache == 0) gcache = sweep_grid_size(dtype, sf32, D, lean, c->sm_count);
+            int64_t need = (P + 1023) / 1024;
+            if (need < 1) need = 1;
+            wgrid = (int)(need < gcache ? need : gcache);
+        }
+        if (!cluster && getenv("AMC_SWEEP_DEBUG")) {
+            const int gcache = c->sweep_grid_cache[lean ? 3 : (sf32 ? 2 : dtype)][D];
             static int told = 0;
             if (!told++) fprintf(stderr, "libamc sweep debug: cooperative grid %d (resident capacity %d on %d SMs), P=%lld\n", wgrid, gcache,
                                  c->sm_count, (long long)P);
@@ -1114,7 +1134,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         }
         if ((rc = ensure(c->partials, (size_t)wgrid * kAccStride * 8))) return rc;
         const size_t sync_bytes = (size_t)(kSyncTickets + n_passes + 32) * 4;
-        if ((rc = ensure(c->syncbuf, sync_bytes))) return rc;
+        if (!cluster && (rc = ensure(c->syncbuf, sync_bytes))) return rc;
         const size_t tab_bytes = nrow * (sizeof(SweepTab) + sizeof(SolverTab));
         if ((rc = ensure(c->tabs, tab_bytes))) return rc;
         std::vector<unsigned char> tab_h(tab_bytes);
@@ -1130,8 +1150,17 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
             st[t].sigma = 1.0 / (1.0 / p->sigma[t]);       // the scale the kernels effectively use
             st[t].pad = 0.0;
         }
-        CU(cudaMemcpyAsync(c->tabs.p, tab_h.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemsetAsync(c->syncbuf.p, 0, sync_bytes, c->stream));
+        // the tables of a sweep depend on (r, dt, n) and the path set's column maps only: pricing the same set again (the
+        // latency regime the cluster kernel exists for) finds them on the device already
+        const bool tabs_cached = cluster && c->tabs_host.size() == tab_bytes + sizeof(void*) &&
+                                 memcmp(c->tabs_host.data(), tab_h.data(), tab_bytes) == 0 &&
+                                 memcmp(c->tabs_host.data() + tab_bytes, &c->tabs.p, sizeof(void*)) == 0;
+        if (!tabs_cached) {
+            CU(cudaMemcpyAsync(c->tabs.p, tab_h.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+            c->tabs_host.assign(tab_h.begin(), tab_h.end());
+            c->tabs_host.insert(c->tabs_host.end(), (const unsigned char*)&c->tabs.p, (const unsigned char*)&c->tabs.p + sizeof(void*));
+        }
+        if (!cluster) CU(cudaMemsetAsync(c->syncbuf.p, 0, sync_bytes, c->stream));
         int32_t* Lstate = nullptr;
         if (lean) {
             if ((rc = ensure(c->lstate, (size_t)ldp * 4))) return rc;
@@ -1150,7 +1179,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         wa.tab = (const SweepTab*)c->tabs.p;
         wa.gamma = dg + off_gamma;
         wa.partials = (double*)c->partials.p;
-        wa.sync = (uint32_t*)c->syncbuf.p;
+        wa.sync = cluster ? nullptr : (uint32_t*)c->syncbuf.p;
         wa.n_paths = P;
         wa.n_steps = n;
         wa.n_passes = n_passes;
@@ -1169,7 +1198,8 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         so.spec = sspec;
         // inside the sweep kernel the scalar routine runs under the streaming loop's register cap (it spills): the
         // warp-cooperative routine takes every step it can certify, at every degree
-        if (opt_warp_solve < 0) so.spec.warp_solve = 1;
+        // (the cluster kernel runs one block per SM with the registers of the dedicated solve kernel: its rule applies)
+        if (opt_warp_solve < 0 && !cluster) so.spec.warp_solve = 1;
         so.gamma = dg + off_gamma;
         so.beta = dg + off_beta;
         so.sv = dg + off_sv;
@@ -1190,11 +1220,25 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         wa.solve_tab = (const SolverTab*)((const char*)c->tabs.p + nrow * sizeof(SweepTab));
 
         CU(cudaEventRecord(c->ev_k0, c->stream));
-        CU(launch_sweep(dtype, sf32, D, lean, wgrid, wa, c->stream));
+        if (cluster) {
+            const cudaError_t ce = launch_cluster_sweep(dtype, sf32, D, wa, c->stream);
+            if (ce != cudaSuccess) {
+                // not fatal: the launch chain prices the same set; this combination is not tried again
+                cudaGetLastError();
+                fprintf(stderr, "libamc: one-cluster sweep unavailable (%s); small path sets take the launch chain\n",
+                        cudaGetErrorString(ce));
+                c->cluster_cap[sf32 ? 2 : dtype][D] = 0;
+                used_cluster = false;
+                chain_fallback = true;
+            }
+        } else {
+            CU(launch_sweep(dtype, sf32, D, lean, wgrid, wa, c->stream));
+        }
         CU(cudaEventRecord(c->ev_k1, c->stream));
-        n_step = 1;
+        n_step = chain_fallback ? 0 : 1;
         n_solve = 0;
-    } else
+    }
+    if (!persistent || chain_fallback)
     {
     if (!regress) {
         // no early exercise and nobody wants continuation values: the price is the discounted mean payoff
@@ -1324,10 +1368,11 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
             CU(cudaEventElapsedTime(&ms, solve_ev[i], solve_ev[i + 1]));
             timing->solve_kernel_ms += ms;
         }
-        if (used_persistent) CU(cudaEventElapsedTime(&timing->step_kernel_ms, c->ev_k0, c->ev_k1));
+        if (used_persistent || used_cluster) CU(cudaEventElapsedTime(&timing->step_kernel_ms, c->ev_k0, c->ev_k1));
         timing->step_launches = n_step;
         timing->solve_launches = n_solve;
         timing->other_launches = n_other;
+        timing->sweep_kind = used_cluster ? 2 : (used_persistent ? 1 : 0);
     }
     return AMC_OK;
 }

@@ -147,6 +147,11 @@ int sweep_grid_size(int dtype, int state_f32, int degree, int lean, int sm_count
 cudaError_t launch_sweep(int dtype, int state_f32, int degree, int lean, int grid, const SweepArgs& a, cudaStream_t s);
 
 
+// one-cluster sweep for small path sets (lsm_cluster.cuh): the largest local path count it takes for this storage /
+// state / degree on the current device (0: unavailable), and its launch (grid = one cluster)
+int64_t cluster_sweep_capacity(int dtype, int state_f32, int degree);
+cudaError_t launch_cluster_sweep(int dtype, int state_f32, int degree, const SweepArgs& a, cudaStream_t s);
+
 int step_grid_size(int dtype, int state_f32, int degree, int sm_count);
 // pdl: launch as a programmatic dependent of the previous kernel in the stream (see common.cuh)
 cudaError_t launch_step(int dtype, int state_f32, int degree, int grid, const StepArgs& a, cudaStream_t s,

@@ -1,0 +1,329 @@
+// Small path sets: the whole backward sweep inside ONE thread-block cluster (sm_100a).
+//
+// Below a few hundred thousand paths a step of the launch chain (lsm_step.cuh -> lsm_solve_kernel) costs 6-8 us, almost
+// all of it the two grid hand-offs; the grid-wide persistent kernel (lsm_sweep.cuh) replaces them by hand-offs through L2
+// and is no faster (profiles/r2_persistent_vs_chain.md).  What is left is hardware that synchronises without L2: a
+// cluster of up to 16 CTAs on the SMs of one GPC.
+//
+//   * the per-path state U and two path columns live in the CTAs' shared memory for the whole sweep (CTA r owns the
+//     paths [r * slice, (r + 1) * slice)); every column is fetched from global memory exactly once, by one 1-D bulk copy
+//     per CTA (cp.async.bulk + mbarrier) issued a whole pass before it is needed: column t-2 replaces column t as soon as
+//     the pass of step t is through its loop, and lands while that pass reduces and solves;
+//   * pass t: decide(t) + moments(t-1) from shared memory (the arithmetic of the step kernel: path_step /
+//     fast_path_step), block reduction into this CTA's row, ONE barrier.cluster, then EVERY CTA gathers the rows of all
+//     CTAs through distributed shared memory in rank order and runs the k x k solve itself (same inputs, same code, same
+//     bits) -- no broadcast, no second barrier; rows are double-buffered by pass parity;
+//   * CTA 0 copies the regression diagnostics of the step and, after the last pass, the price to global memory; every CTA
+//     writes its slice of the state back once at the end.
+//
+// No spin loops, no global flags: the only waits are mbarriers on the CTA's own copies and the hardware cluster barrier.
+// Capacity is what 16 x ~215 KB of shared memory hold (2 columns + state per path): ~140k paths f64/f64, ~280k f32/f32;
+// larger sets take the launch chain.
+#pragma once
+#include "kernels.h"
+#include "lsm_solve_block.cuh"
+#include "lsm_step.cuh"
+
+namespace amc {
+
+constexpr int kClusterThreads = kSolveThreads;      // solve_block() is written for this block size
+constexpr int kClusterMaxCtas = 16;
+
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_cta_count() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs of the cluster; orders shared-memory writes before it against reads (local or remote) after it
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_remote_shared_f64(const double* local, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr(local)), "r"(cta));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+// paths per CTA: an equal share, padded to 32 elements like the columns themselves (bulk copies are 128-byte granular)
+__host__ __device__ inline int64_t cluster_slice(int64_t n_paths, int n_ctas) {
+    return ((n_paths + n_ctas - 1) / n_ctas + 31) / 32 * 32;
+}
+template <typename XT, typename UT>
+constexpr size_t cluster_bytes_per_path() { return 2 * sizeof(XT) + sizeof(UT); }
+
+template <typename XT, typename UT, int D>
+__global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const __grid_constant__ SweepArgs a) {
+    constexpr int K = D + 1;
+    constexpr int NACC = 3 * D + 1;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ double red[(kClusterThreads / 32) * NACC];
+    __shared__ __align__(16) double rows[2][kAccStride];      // this CTA's partial sums of pass p: rows[p & 1]
+    __shared__ double sums_sh[kAccStride];
+    __shared__ double o_gamma[kMaxK], o_beta[kMaxK], o_sv[kMaxK], o_ms[4], o_price[1];
+    __shared__ int o_rank[1];
+    __shared__ uint64_t full[2];                              // column t lands in buffer t & 1
+
+    const uint32_t cta = cluster_cta_rank(), n_ctas = cluster_cta_count();
+    const int64_t slice = cluster_slice(a.n_paths, (int)n_ctas);
+    const int64_t p_lo = (int64_t)cta * slice;
+    int64_t left = a.n_paths - p_lo;
+    const int cnt = (int)(left < 0 ? 0 : (left > slice ? slice : left));
+    const uint32_t col_bytes = (uint32_t)((cnt + 31) / 32 * 32) * (uint32_t)sizeof(XT);
+
+    XT* const xs0 = reinterpret_cast<XT*>(dyn);
+    XT* const xs1 = xs0 + slice;
+    UT* const us = reinterpret_cast<UT*>(xs1 + slice);
+    const int n = a.n_steps;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // thread 0: fetch column t into its buffer
+    auto fetch = [&](int t) {
+        if (cnt == 0) return;
+        const XT* src = reinterpret_cast<const XT*>(static_cast<const char*>(a.S) + (size_t)t * (size_t)a.ld * sizeof(XT)) + p_lo;
+        mbar_expect_tx(&full[t & 1], col_bytes);
+        tma_load_1d((t & 1) ? xs1 : xs0, src, col_bytes, &full[t & 1]);
+    };
+    if (threadIdx.x == 0) {
+        fetch(n);
+        if (a.n_passes > 1 && n >= 1) fetch(n - 1);
+    }
+    FastConsts fc;
+    fc.sgn = a.is_put ? -1.0 : 1.0;
+    fc.sgnK = a.is_put ? a.K : -a.K;
+
+    for (int p = 0; p < a.n_passes; ++p) {
+        const int t = n - p;
+        const int mode = (p == 0) ? kMaturity : (a.american ? kDecide : kObserve);
+        const bool moments = a.n_passes > 1 && t > 0;
+        const bool final_pass = (p == a.n_passes - 1);
+        const SweepTab td = a.tab[t];
+        const SweepTab tr = moments ? a.tab[t - 1] : td;
+        double gam[D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i) gam[i] = (mode == kDecide) ? o_gamma[i] : 0.0;     // left by the solve of pass p-1
+
+        StepArgs sa = {};                        // the launch-uniform view path_step() expects
+        sa.t_dec = t;
+        sa.mode = mode;
+        sa.moments = moments ? 1 : 0;
+        sa.is_put = a.is_put;
+        sa.K = a.K;
+        sa.disc_dec = td.disc;
+        sa.mu_dec = td.mu; sa.isg_dec = td.isg;
+        sa.mu_reg = tr.mu; sa.isg_reg = tr.isg;
+        fc.da = td.isg; fc.db = -td.mu * td.isg;
+        fc.ra = tr.isg; fc.rb = -tr.mu * tr.isg;
+        fc.disc = td.disc;
+        const bool fast_ok = (mode == kDecide) && moments && !a.first_hit;
+
+        const XT* const xd = (t & 1) ? xs1 : xs0;
+        const XT* const xr = (t & 1) ? xs0 : xs1;
+        if (cnt > 0) {
+            // column t is the ((n - t) / 2)-th copy into its buffer (waiting twice for the same copy is fine: no later
+            // copy into that buffer has been issued yet)
+            mbar_wait(&full[t & 1], (uint32_t)((n - t) >> 1) & 1u);
+            if (moments) mbar_wait(&full[(t - 1) & 1], (uint32_t)((n - t + 1) >> 1) & 1u);
+        }
+        double acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+#pragma unroll 2
+        for (int j = threadIdx.x; j < cnt; j += kClusterThreads) {
+            const double x_dec = (double)xd[j];
+            const double x_reg = moments ? (double)xr[j] : 0.0;
+            double u = (p != 0) ? (double)us[j] : 0.0;
+            bool changed;
+            int tau_j = t;
+            if (fast_ok) {
+                changed = fast_path_step<D>(fc, gam, x_dec, x_reg, u, true, acc);
+            } else {
+                const int fh = a.first_hit ? __ldg(a.first_hit + p_lo + j) : 0;
+                changed = path_step<D>(sa, gam, x_dec, x_reg, u, tau_j, fh, acc);
+            }
+            if (changed) {
+                us[j] = (UT)u;
+                if (a.tau) a.tau[p_lo + j] = t;
+            }
+        }
+        __syncthreads();                         // everybody is through with column t: its buffer takes column t-2
+        if (threadIdx.x == 0 && a.n_passes > 1 && t >= 2) fetch(t - 2);
+
+        block_reduce_store<NACC, kClusterThreads, kAccStride>(acc, red, rows[p & 1]);
+        cluster_barrier();                       // every CTA's row of this pass is complete and visible
+
+        if (threadIdx.x < kAccStride) {
+            double part[kClusterMaxCtas];
+#pragma unroll
+            for (int q = 0; q < kClusterMaxCtas; ++q)
+                part[q] = (q < (int)n_ctas && threadIdx.x < NACC) ? ld_remote_shared_f64(&rows[p & 1][threadIdx.x], (uint32_t)q) : 0.0;
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < kClusterMaxCtas; ++q) tot += part[q];      // rank order: the same bits in every CTA
+            sums_sh[threadIdx.x] = tot;
+            if (threadIdx.x < kMaxK) { o_gamma[threadIdx.x] = 0.0; o_beta[threadIdx.x] = 0.0; o_sv[threadIdx.x] = 0.0; }
+            if (threadIdx.x < 4) o_ms[threadIdx.x] = 0.0;
+            if (threadIdx.x == 0) o_rank[0] = 0;
+        }
+        __syncthreads();
+
+        const int row = final_pass ? 0 : t - 1;
+        SolveArgs sv = {};
+        sv.sums = sums_sh;
+        sv.do_reduce = 0;
+        sv.do_solve = final_pass ? 0 : 1;
+        sv.final_price = final_pass ? 1 : 0;
+        sv.spec = a.solve.spec;
+        if (final_pass) {
+            sv.y_scale = 1.0; sv.mu_ref = 0.0; sv.sigma_ref = 1.0;
+        } else {
+            const SolverTab tb = a.solve_tab[row];
+            sv.y_scale = tb.y_scale; sv.mu_ref = tb.mu; sv.sigma_ref = tb.sigma;
+        }
+        sv.gamma = o_gamma; sv.beta = o_beta; sv.sv = o_sv; sv.mean_std = o_ms; sv.rank = o_rank; sv.price = o_price;
+        sv.n_batch = 1;
+        solve_block<K, false>(sv, sv, 0u, nullptr);          // ends with a block barrier: o_* are complete
+
+        if (cta == 0) {
+            if (final_pass) {
+                if (threadIdx.x == 0) {
+                    a.solve.price[0] = o_price[0];
+                    a.solve.sums[2 * D] = sums_sh[2 * D];
+                }
+            } else if (threadIdx.x < kMaxK) {
+                const size_t o = (size_t)row * kMaxK + threadIdx.x;
+                a.solve.gamma[o] = o_gamma[threadIdx.x];
+                if (a.solve.beta) a.solve.beta[o] = o_beta[threadIdx.x];
+                if (a.solve.sv) a.solve.sv[o] = o_sv[threadIdx.x];
+                if (threadIdx.x < 3 && a.solve.mean_std) a.solve.mean_std[(size_t)row * 3 + threadIdx.x] = o_ms[threadIdx.x];
+                if (threadIdx.x == 0 && a.solve.rank) a.solve.rank[row] = o_rank[0];
+            }
+        }
+    }
+    // the state goes back to global memory once (cashflows are an output of the sweep)
+    UT* const Ug = static_cast<UT*>(a.U) + p_lo;
+    for (int j = threadIdx.x; j < cnt; j += kClusterThreads) Ug[j] = us[j];
+    cluster_barrier();                           // nobody leaves while a neighbour may still be reading its rows
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: capacity query and launch
+struct ClusterPlan {
+    int n_ctas = 0;             // 0: this kernel cannot run here (no cluster of >= 2 CTAs with the shared memory it needs)
+    size_t dyn_max = 0;         // dynamic shared memory per CTA the kernel may use
+    int64_t max_paths = 0;
+};
+
+template <typename XT, typename UT, int D>
+static const ClusterPlan& cluster_plan_t() {
+    static ClusterPlan plan;
+    static bool done = false;
+    if (done) return plan;
+    done = true;
+    auto kernel = lsm_cluster_kernel<XT, UT, D>;
+    cudaFuncAttributes fa;
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaFuncGetAttributes(&fa, kernel) != cudaSuccess ||
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return plan;
+    }
+    const int64_t dyn = ((int64_t)optin - (int64_t)fa.sharedSizeBytes - 1024) / 128 * 128;
+    if (dyn < 16384) return plan;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess ||
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return plan;
+    }
+    for (int nc = kClusterMaxCtas; nc >= 2; nc /= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nc);
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.dynamicSmemBytes = (size_t)dyn;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = nc;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kernel, &cfg) == cudaSuccess && n_clusters >= 1) {
+            plan.n_ctas = nc;
+            plan.dyn_max = (size_t)dyn;
+            const int64_t slice_max = (dyn / (int64_t)cluster_bytes_per_path<XT, UT>()) / 32 * 32;
+            plan.max_paths = slice_max * nc;
+            break;
+        }
+        cudaGetLastError();
+    }
+    return plan;
+}
+
+template <typename XT, typename UT, int D>
+static cudaError_t launch_cluster_t(const SweepArgs& a, cudaStream_t s) {
+    const ClusterPlan& plan = cluster_plan_t<XT, UT, D>();
+    if (plan.n_ctas == 0 || a.n_paths > plan.max_paths || a.n_paths < 1) return cudaErrorInvalidConfiguration;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.n_ctas);
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = (size_t)cluster_slice(a.n_paths, plan.n_ctas) * cluster_bytes_per_path<XT, UT>();
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan.n_ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, lsm_cluster_kernel<XT, UT, D>, a);
+}
+
+template <typename XT, typename UT>
+static cudaError_t launch_cluster_d(int degree, const SweepArgs& a, cudaStream_t s) {
+    switch (degree) {
+        case 0: return launch_cluster_t<XT, UT, 0>(a, s);
+        case 1: return launch_cluster_t<XT, UT, 1>(a, s);
+        case 2: return launch_cluster_t<XT, UT, 2>(a, s);
+        case 3: return launch_cluster_t<XT, UT, 3>(a, s);
+        case 4: return launch_cluster_t<XT, UT, 4>(a, s);
+        case 5: return launch_cluster_t<XT, UT, 5>(a, s);
+        case 6: return launch_cluster_t<XT, UT, 6>(a, s);
+        case 7: return launch_cluster_t<XT, UT, 7>(a, s);
+        case 8: return launch_cluster_t<XT, UT, 8>(a, s);
+        case 9: return launch_cluster_t<XT, UT, 9>(a, s);
+        case 10: return launch_cluster_t<XT, UT, 10>(a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename XT, typename UT>
+static int64_t cluster_capacity_d(int degree) {
+    switch (degree) {
+        case 0: return cluster_plan_t<XT, UT, 0>().max_paths;
+        case 1: return cluster_plan_t<XT, UT, 1>().max_paths;
+        case 2: return cluster_plan_t<XT, UT, 2>().max_paths;
+        case 3: return cluster_plan_t<XT, UT, 3>().max_paths;
+        case 4: return cluster_plan_t<XT, UT, 4>().max_paths;
+        case 5: return cluster_plan_t<XT, UT, 5>().max_paths;
+        case 6: return cluster_plan_t<XT, UT, 6>().max_paths;
+        case 7: return cluster_plan_t<XT, UT, 7>().max_paths;
+        case 8: return cluster_plan_t<XT, UT, 8>().max_paths;
+        case 9: return cluster_plan_t<XT, UT, 9>().max_paths;
+        case 10: return cluster_plan_t<XT, UT, 10>().max_paths;
+    }
+    return 0;
+}
+
+}  // namespace amc

@@ -24,6 +24,12 @@ int sweep_occupancy_f32(int degree);
 int sweep_occupancy_f64(int degree);
 int sweep_occupancy_f32s(int degree);
 int sweep_occupancy_lean(int state_f32, int degree);
+cudaError_t launch_cluster_f32(int degree, const SweepArgs& a, cudaStream_t s);
+cudaError_t launch_cluster_f64(int degree, const SweepArgs& a, cudaStream_t s);
+cudaError_t launch_cluster_f32s(int degree, const SweepArgs& a, cudaStream_t s);
+int64_t cluster_capacity_f32(int degree);
+int64_t cluster_capacity_f64(int degree);
+int64_t cluster_capacity_f32s(int degree);
 
 // ---------------------------------------------------------------------------------------------------------
 // Solve kernel: <<<1, 128>>>.
@@ -160,6 +166,18 @@ int sweep_grid_size(int dtype, int state_f32, int degree, int lean, int sm_count
     else nb = dtype == 1 ? (state_f32 ? sweep_occupancy_f32s(degree) : sweep_occupancy_f32(degree)) : sweep_occupancy_f64(degree);
     if (nb < 1) nb = 1;
     return sm_count * nb;                                  // cooperative launch: every block resident
+}
+
+cudaError_t launch_cluster_sweep(int dtype, int state_f32, int degree, const SweepArgs& a, cudaStream_t s) {
+    if (dtype == 1 && state_f32) return launch_cluster_f32s(degree, a, s);
+    if (state_f32) return cudaErrorInvalidValue;
+    return dtype == 1 ? launch_cluster_f32(degree, a, s) : launch_cluster_f64(degree, a, s);
+}
+
+int64_t cluster_sweep_capacity(int dtype, int state_f32, int degree) {
+    if (dtype == 1 && state_f32) return cluster_capacity_f32s(degree);
+    if (state_f32) return 0;
+    return dtype == 1 ? cluster_capacity_f32(degree) : cluster_capacity_f64(degree);
 }
 
 cudaError_t launch_solve(const SolveArgs& a, cudaStream_t s, bool pdl) {

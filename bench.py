@@ -383,8 +383,10 @@ def measure(rt, name, wl, steps, warmup, lean=False, want_e2e=True, sampler=None
     dfma_per_path_step = 3 * D + 2 + 8 + D
     fma_rate = P_local * float(n) * dfma_per_path_step / (step_ms * 1e-3)
     price = float(res_dev[-1].price)
-    kern = ("lsm_sweep_kernel (persistent: exercise decision + regression moments of all passes, solve by the last block "
-            "of every pass)") if launches == 1 else "lsm_step_tma_kernel (fused exercise decision + regression moments)"
+    kern = {1: "lsm_sweep_kernel (persistent: exercise decision + regression moments of all passes, solve by the last "
+               "block of every pass)",
+            2: "lsm_cluster_kernel (one 16-CTA cluster: state and columns in shared memory, all passes, solve in every CTA)"
+            }.get(tm.get("sweep_kind", 0), "lsm_step_tma_kernel (fused exercise decision + regression moments)")
     out = dict(
         value=value, ms_per_step=ms_dev / steps, steps=steps, warmup=warmup, scaling="strong" if strong else "weak",
         dtype="f64" if did == N.F64 else "f64 sums over f32 paths (%s state)" % wl["state"], data=data,

@@ -159,6 +159,8 @@ typedef struct amc_lsm_timing {
     int step_launches;
     int solve_launches;
     int other_launches;
+    int sweep_kind;        /* which kernels ran the sweep: 0 = per-step launch chain, 1 = persistent cooperative kernel
+                              (path-free sets, AMC_PERSISTENT=1), 2 = one-cluster kernel (small stored sets) */
 } amc_lsm_timing;
 
 /* Price one contract on a device-resident path set.  `price` is the GLOBAL mean over all ranks' paths.

@@ -38,3 +38,112 @@ def test_persistent_sweep_on_stored_sets_stays_correct(libamc_path):
     env = dict(os.environ, AMC_PERSISTENT="1", PYTHONPATH=ROOT)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert p.returncode == 0 and "persistent ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+# ---- one-cluster sweep kernel (lsm_cluster.cuh): what prices small stored sets by default ------------------------------
+CLUSTER_CASES = [
+    # name, P, n, dtype, state, contract kwargs, basis, degree, lsm kwargs
+    ("put_f64", 30011, 20, "float64", "float64", dict(), "Power", 3, dict()),
+    ("put_barrier_f64", 30011, 20, "float64", "float64", dict(barrier=33.0), "Power", 3, dict()),
+    ("european_f64", 30011, 20, "float64", "float64", dict(ex="European"), "Chebyshev", 4, dict()),
+    ("call_scaled_f64", 12345, 7, "float64", "float64", dict(opt="Call", K=34.0), "Legendre", 6, dict(scaling=True)),
+    ("put_deg8_scaled_f64", 20000, 10, "float64", "float64", dict(), "Laguerre", 8, dict(scaling=True)),
+    ("put_deg0_f64", 999, 5, "float64", "float64", dict(), "Power", 0, dict()),
+    ("put_deg1_f64", 31, 3, "float64", "float64", dict(), "Power", 1, dict()),
+    ("put_f32paths", 30011, 20, "float32", "float64", dict(), "Power", 3, dict()),
+    ("put_f32state", 30011, 20, "float32", "float32", dict(), "Power", 3, dict()),
+    ("put_cheb4_unscaled_f64", 25000, 12, "float64", "float64", dict(), "Chebyshev", 4, dict()),   # rank-truncated steps
+]
+
+_CLUSTER_WORKER = r"""
+import sys, numpy as np, american_monte_carlo_b200 as amc
+sys.path.insert(0, %(tests)r)
+from test_gpu_small_shapes import CLUSTER_CASES
+out = {}
+for name, P, n, dtype, state, ckw, basis, deg, kw in CLUSTER_CASES:
+    Z = np.random.default_rng(P + n).standard_normal((P, n))
+    dp = amc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0, dtype=dtype)
+    r = amc.lsm_price(dp, ckw.get('K', 40.0), 0.06, 1.0 / n, ckw.get('opt', 'Put'), ckw.get('barrier'), ckw.get('ex', 'American'),
+                      basis, deg, want_exercise_steps=True, want_cashflows=True, want_regression=True, state_dtype=state, **kw)
+    out[name + '.price'] = np.float64(r.price)
+    out[name + '.kind'] = np.int64(r.timing['sweep_kind'])
+    out[name + '.steps'] = r.exercise_steps
+    out[name + '.cash'] = r.cashflow0
+    out[name + '.gamma'] = r.gamma
+    out[name + '.rank'] = r.rank
+    dp.free()
+np.savez(sys.argv[1], **out)
+print('worker ok')
+"""
+
+
+def _run_cluster_worker(tmp_path, tag, env_extra):
+    import subprocess
+    import numpy as np
+    out = os.path.join(str(tmp_path), tag + ".npz")
+    env = dict(os.environ, PYTHONPATH=ROOT, **env_extra)
+    code = _CLUSTER_WORKER % dict(tests=os.path.join(ROOT, "tests"))
+    p = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0 and "worker ok" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
+    return dict(np.load(out))
+
+
+def test_cluster_kernel_equals_launch_chain_and_oracle(amc, tmp_path):
+    """Small stored sets are priced by the one-cluster kernel (sweep_kind 2); AMC_CLUSTER=0 keeps them on the launch chain
+    (sweep_kind 0).  Same decisions on every path, prices to rounding (the partial sums are grouped differently), same
+    regression ranks, coefficient tables to 1e-9; and the cluster result against the oracle on the f64 cases."""
+    import numpy as np
+    from oracle import lsm_oracle as orc
+    a = _run_cluster_worker(tmp_path, "cluster", {"AMC_CLUSTER": "1"})
+    b = _run_cluster_worker(tmp_path, "chain", {"AMC_CLUSTER": "0"})
+    for name, P, n, dtype, state, ckw, basis, deg, kw in CLUSTER_CASES:
+        assert int(a[name + ".kind"]) == 2, (name, "not priced by the cluster kernel")
+        assert int(b[name + ".kind"]) == 0, name
+        flips = int((a[name + ".steps"] != b[name + ".steps"]).sum())
+        assert flips == 0, (name, flips)
+        pa, pb = float(a[name + ".price"]), float(b[name + ".price"])
+        tol = 1e-12 if state == "float64" else 1e-7
+        assert abs(pa - pb) <= tol * abs(pb), (name, pa, pb)
+        np.testing.assert_array_equal(a[name + ".rank"], b[name + ".rank"], err_msg=name)
+        if state == "float64":
+            np.testing.assert_array_equal(a[name + ".cash"], b[name + ".cash"], err_msg=name)
+        if bool((b[name + ".rank"][:n] == deg + 1).all()):       # rank-truncated fits amplify rounding: decisions above
+            np.testing.assert_allclose(a[name + ".gamma"], b[name + ".gamma"], rtol=1e-7, atol=1e-9, err_msg=name)
+        if dtype == "float64":
+            Z = np.random.default_rng(P + n).standard_normal((P, n))
+            paths = orc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0)
+            want = orc.lsm_backward(paths, ckw.get("K", 40.0), 0.06, 1.0 / n, ckw.get("opt", "Put"), ckw.get("barrier"),
+                                    ckw.get("ex", "American"), basis, deg, keep_continuation=False, **kw)
+            assert int((a[name + ".steps"] != want.exercise_times).sum()) == 0, name
+            assert abs(pa - want.price) <= 1e-10 * abs(want.price), (name, pa, want.price)
+
+
+def test_cluster_kernel_capacity_edge(amc):
+    """Path counts around what one cluster's shared memory holds: the largest set the cluster kernel takes and the first
+    one that goes to the launch chain agree with the oracle alike (3 steps keep the oracle quick)."""
+    import numpy as np
+    from oracle import lsm_oracle as orc
+    n = 3
+    kinds = []
+    for P in (150_000, 151_040, 151_041, 152_000):
+        Z = np.random.default_rng(P).standard_normal((P, n))
+        paths = orc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0)
+        want = orc.lsm_backward(paths, 40.0, 0.06, 1.0 / n, "Put", None, "American", "Power", 3, keep_continuation=False)
+        dp = amc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0)
+        res = amc.lsm_price(dp, 40.0, 0.06, 1.0 / n, "Put", None, "American", "Power", 3, want_exercise_steps=True)
+        kinds.append(res.timing["sweep_kind"])
+        assert int((res.exercise_steps != want.exercise_times).sum()) == 0, P
+        assert abs(res.price - want.price) <= 1e-10 * want.price, (P, res.price, want.price)
+        dp.free()
+    assert kinds[0] == 2 and kinds[-1] == 0, kinds      # both routes were exercised
+    assert kinds == sorted(kinds, reverse=True), kinds  # one threshold
+
+
+def test_launch_chain_on_ragged_small_shapes(libamc_path):
+    """The walk of test_all_kernels_on_ragged_small_shapes again with the cluster kernel switched off: the launch chain
+    (and its CUDA-graph replay) stays covered on small shapes."""
+    import subprocess
+    env = dict(os.environ, AMC_CLUSTER="0", PYTHONPATH=ROOT)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sanitize_small.py")], capture_output=True, text=True,
+                       timeout=900, env=env, cwd=ROOT)
+    assert p.returncode == 0 and "sanitize_small: ok" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
