@@ -965,6 +965,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     sspec.want_svd = spec->want_svd;
     sspec.scaling_factor = spec->scaling_factor;
     sspec.n_paths = Pg;
+    sspec.inv_n_paths = Pg > 0.0 ? 1.0 / Pg : 0.0;
     static const int opt_warp_solve = getenv("AMC_WARP_SOLVE") ? atoi(getenv("AMC_WARP_SOLVE")) : -1;
     sspec.warp_solve = opt_warp_solve < 0 ? (D >= 6) : opt_warp_solve;    // scalar registers win up to k = 6
 
@@ -1095,7 +1096,10 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
     if (C == 1 && !exchange && !p->lean && !opt_persistent && opt_cluster && P >= 1) {
         int64_t& cap = c->cluster_cap[sf32 ? 2 : dtype][D];
         if (cap < 0) cap = cluster_sweep_capacity(dtype, sf32, D);
-        cluster = P <= cap;
+        // what the cluster's shared memory holds is more than what it prices faster than the chain: the 16 SMs of the
+        // cluster stream a pass at FP64-pipe speed, the chain's 148 do not care (profiles/r2_cluster_vs_chain.md)
+        static const long long opt_cluster_max = getenv("AMC_CLUSTER_MAX_PATHS") ? atoll(getenv("AMC_CLUSTER_MAX_PATHS")) : 131072;
+        cluster = P <= cap && P <= opt_cluster_max;
     }
     const bool persistent = C == 1 && (opt_persistent || p->lean || cluster) && (!exchange || c->transport == 2);
     if (p->lean && !persistent)
@@ -1180,6 +1184,13 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         wa.gamma = dg + off_gamma;
         wa.partials = (double*)c->partials.p;
         wa.sync = cluster ? nullptr : (uint32_t*)c->syncbuf.p;
+        // AMC_CLUSTER_TRACE=1: the cluster kernel writes CTA 0's SM clock at 8 points of every pass (debug aid)
+        static const int opt_trace = getenv("AMC_CLUSTER_TRACE") ? atoi(getenv("AMC_CLUSTER_TRACE")) : 0;
+        if (cluster && opt_trace) {
+            if ((rc = ensure(c->syncbuf, (size_t)n_passes * 64))) return rc;
+            CU(cudaMemsetAsync(c->syncbuf.p, 0, (size_t)n_passes * 64, c->stream));
+            wa.sync = (uint32_t*)c->syncbuf.p;
+        }
         wa.n_paths = P;
         wa.n_steps = n;
         wa.n_passes = n_passes;
@@ -1328,6 +1339,24 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         if ((rc = sync_with_nccl_watchdog(c))) return rc;
     } else {
         CU(cudaStreamSynchronize(c->stream));
+    }
+    if (used_cluster && getenv("AMC_CLUSTER_TRACE") && atoi(getenv("AMC_CLUSTER_TRACE")) && n >= 4) {
+        static int traced = 0;
+        if (++traced == 8) {                 // once, on a warm call
+            const int np = regress ? n + 1 : 1;
+            std::vector<long long> tr((size_t)np * 8);
+            cudaMemcpy(tr.data(), c->syncbuf.p, tr.size() * 8, cudaMemcpyDeviceToHost);
+            double d[8] = {};
+            int cntp = 0;
+            for (int q = 2; q + 2 < np; ++q, ++cntp) {
+                for (int k = 0; k < 7; ++k) d[k] += (double)(tr[q * 8 + k + 1] - tr[q * 8 + k]);
+                d[7] += (double)(tr[(q + 1) * 8] - tr[q * 8 + 7]);
+            }
+            fprintf(stderr, "libamc cluster trace (SM cycles per pass, mean over %d passes; P=%lld D=%d): top->waited %.0f | loop %.0f | "
+                            "block reduce %.0f | cluster barrier %.0f | gather %.0f | solve %.0f | outputs %.0f | loop-back %.0f\n",
+                    cntp, (long long)P, D, d[0] / cntp, d[1] / cntp, d[2] / cntp, d[3] / cntp, d[4] / cntp, d[5] / cntp, d[6] / cntp,
+                    d[7] / cntp);
+        }
     }
     if (abort_h && getenv("AMC_SWEEP_DEBUG")) {
         std::vector<uint32_t> w(kSyncTickets + 8);
@@ -1676,6 +1705,7 @@ static int regression_fit_impl(amc_ctx* c, const double* X, const double* Y, Pre
     s.spec.want_svd = 0;
     s.spec.scaling_factor = scaling_factor;
     s.spec.n_paths = (double)n;
+    s.spec.inv_n_paths = n > 0 ? 1.0 / (double)n : 0.0;
     s.y_scale = 1.0;
     s.mu_ref = px->mu[0];
     s.sigma_ref = 1.0 / a.isg_reg;

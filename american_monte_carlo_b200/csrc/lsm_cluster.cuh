@@ -20,6 +20,8 @@
 // Capacity is what 16 x ~215 KB of shared memory hold (2 columns + state per path): ~140k paths f64/f64, ~280k f32/f32;
 // larger sets take the launch chain.
 #pragma once
+#include <type_traits>
+
 #include "kernels.h"
 #include "lsm_solve_block.cuh"
 #include "lsm_step.cuh"
@@ -27,6 +29,7 @@
 namespace amc {
 
 constexpr int kClusterThreads = kSolveThreads;      // solve_block() is written for this block size
+static_assert(kClusterThreads == 256, "the block reduction of lsm_cluster_kernel adds 8 warps pairwise");
 constexpr int kClusterMaxCtas = 16;
 
 __device__ __forceinline__ uint32_t cluster_cta_rank() {
@@ -43,12 +46,49 @@ __device__ __forceinline__ uint32_t cluster_cta_count() {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ double ld_remote_shared_f64(const double* local, uint32_t cta) {
+// store into the shared memory of CTA `cta` of the cluster, at the address `local` has in this CTA
+__device__ __forceinline__ void st_remote_shared_f64(double* local, uint32_t cta, double v) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr(local)), "r"(cta));
-    double v;
-    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
-    return v;
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// Sum N per-lane values over the 32 lanes of a warp by recursive halving: at every stage a lane hands half of its vector
+// to the partner lane and adds what it receives to the half it keeps -- NP - 1 + log2(32 / NP) shuffles for NP = N rounded
+// up to a power of two, instead of 5 N butterflies.  On return v[0] of lane l is the warp total of accumulator
+// warp_sum_slot<N>(l) (slots >= N are padding); every accumulator is held by 32 / NP lanes.  Fixed order: deterministic.
+template <int N> struct WarpSumPad { static constexpr int value = N <= 1 ? 1 : (N <= 2 ? 2 : (N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32)))); };
+template <int N>
+__device__ __forceinline__ int warp_sum_slot(int lane) {
+    constexpr int NP = WarpSumPad<N>::value;
+    int slot = 0;
+    // stage k uses lane bit 16 >> k and decides bit (NP / 2) >> k of the slot
+#pragma unroll
+    for (int b = 16, h = NP / 2; h >= 1; b >>= 1, h >>= 1) slot += (lane & b) ? h : 0;
+    return slot;
+}
+template <int N>
+__device__ __forceinline__ double warp_transpose_sum(const double (&acc)[N]) {
+    constexpr int NP = WarpSumPad<N>::value;
+    const int lane = threadIdx.x & 31;
+    double v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) v[i] = (i < N) ? acc[i] : 0.0;
+    int b = 16;
+#pragma unroll
+    for (int len = NP; len > 1; len >>= 1, b >>= 1) {
+        const bool up = (lane & b) != 0;
+#pragma unroll
+        for (int i = 0; i < len / 2; ++i) {
+            const double send = up ? v[i] : v[i + len / 2];
+            const double keep = up ? v[i + len / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, b);
+        }
+    }
+    // the lane bits not used for splitting: plain butterflies on the one value left
+#pragma unroll
+    for (; b >= 1; b >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], b);
+    return v[0];
 }
 
 // paths per CTA: an equal share, padded to 32 elements like the columns themselves (bulk copies are 128-byte granular)
@@ -63,8 +103,10 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
     constexpr int K = D + 1;
     constexpr int NACC = 3 * D + 1;
     extern __shared__ __align__(128) unsigned char dyn[];
-    __shared__ double red[(kClusterThreads / 32) * NACC];
-    __shared__ __align__(16) double rows[2][kAccStride];      // this CTA's partial sums of pass p: rows[p & 1]
+    __shared__ double red[(kClusterThreads / 32) * WarpSumPad<NACC>::value];
+    // rows[p & 1][q] = CTA q's partial sums of pass p, PUSHED here by CTA q before the pass's cluster barrier (every CTA
+    // holds all rows: the remote-store latency is spent inside the barrier, the reads after it are local)
+    __shared__ __align__(16) double rows[2][kClusterMaxCtas][kAccStride];
     __shared__ double sums_sh[kAccStride];
     __shared__ double o_gamma[kMaxK], o_beta[kMaxK], o_sv[kMaxK], o_ms[4], o_price[1];
     __shared__ int o_rank[1];
@@ -102,14 +144,24 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
     FastConsts fc;
     fc.sgn = a.is_put ? -1.0 : 1.0;
     fc.sgnK = a.is_put ? a.K : -a.K;
+    // per-column constants: the entry of column t-1 is the next pass's entry of column t, the one after is fetched a
+    // whole pass ahead (its global-memory latency is off the pass-to-pass critical path)
+    SweepTab td = a.tab[n];
+    SweepTab tr = (a.n_passes > 1 && n >= 1) ? a.tab[n - 1] : td;
+
+    // AMC_CLUSTER_TRACE (api.cu): CTA 0 / thread 0 leaves its SM clock at 8 points of every pass
+    long long* const trace = (cta == 0 && threadIdx.x == 0) ? reinterpret_cast<long long*>(a.sync) : nullptr;
 
     for (int p = 0; p < a.n_passes; ++p) {
         const int t = n - p;
         const int mode = (p == 0) ? kMaturity : (a.american ? kDecide : kObserve);
         const bool moments = a.n_passes > 1 && t > 0;
         const bool final_pass = (p == a.n_passes - 1);
-        const SweepTab td = a.tab[t];
-        const SweepTab tr = moments ? a.tab[t - 1] : td;
+        if (trace) trace[p * 8 + 0] = clock64();
+        const SweepTab tr_next = (a.n_passes > 1 && t >= 2) ? a.tab[t - 2] : tr;
+        SolverTab tb;
+        tb.y_scale = 1.0; tb.mu = 0.0; tb.sigma = 1.0; tb.pad = 0.0;
+        if (!final_pass) tb = a.solve_tab[t - 1];
         double gam[D + 1];
 #pragma unroll
         for (int i = 0; i <= D; ++i) gam[i] = (mode == kDecide) ? o_gamma[i] : 0.0;     // left by the solve of pass p-1
@@ -136,11 +188,41 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
             mbar_wait(&full[t & 1], (uint32_t)((n - t) >> 1) & 1u);
             if (moments) mbar_wait(&full[(t - 1) & 1], (uint32_t)((n - t + 1) >> 1) & 1u);
         }
+        if (trace) trace[p * 8 + 1] = clock64();
         double acc[NACC];
 #pragma unroll
         for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-#pragma unroll 2
-        for (int j = threadIdx.x; j < cnt; j += kClusterThreads) {
+        // Several paths per thread and iteration, loaded first and then stepped: with 8 warps per SM the loop is bound by the
+        // latency of one path's dependent FP64 chain unless several chains are in flight per thread.
+        int j = threadIdx.x;
+        auto fast_chunks = [&](auto ilp_c) {
+            constexpr int kIlp = decltype(ilp_c)::value;
+            for (; j + (kIlp - 1) * kClusterThreads < cnt; j += kIlp * kClusterThreads) {
+                double x_dec[kIlp], x_reg[kIlp], u[kIlp];
+                bool changed[kIlp];
+#pragma unroll
+                for (int k = 0; k < kIlp; ++k) {
+                    x_dec[k] = (double)xd[j + k * kClusterThreads];
+                    x_reg[k] = (double)xr[j + k * kClusterThreads];
+                    u[k] = (double)us[j + k * kClusterThreads];
+                }
+#pragma unroll
+                for (int k = 0; k < kIlp; ++k) changed[k] = fast_path_step<D>(fc, gam, x_dec[k], x_reg[k], u[k], true, acc);
+#pragma unroll
+                for (int k = 0; k < kIlp; ++k) {
+                    if (changed[k]) {
+                        us[j + k * kClusterThreads] = (UT)u[k];
+                        if (a.tau) a.tau[p_lo + j + k * kClusterThreads] = t;
+                    }
+                }
+            }
+        };
+        if (fast_ok) {
+            if (D <= 3) fast_chunks(std::integral_constant<int, 8>{});
+            fast_chunks(std::integral_constant<int, 4>{});
+            fast_chunks(std::integral_constant<int, 2>{});
+        }
+        for (; j < cnt; j += kClusterThreads) {
             const double x_dec = (double)xd[j];
             const double x_reg = moments ? (double)xr[j] : 0.0;
             double u = (p != 0) ? (double)us[j] : 0.0;
@@ -159,24 +241,49 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
         }
         __syncthreads();                         // everybody is through with column t: its buffer takes column t-2
         if (threadIdx.x == 0 && a.n_passes > 1 && t >= 2) fetch(t - 2);
+        if (trace) trace[p * 8 + 2] = clock64();
 
-        block_reduce_store<NACC, kClusterThreads, kAccStride>(acc, red, rows[p & 1]);
+        {
+            // block reduction into this CTA's row: warp totals by recursive halving, then the 8 warps' values pairwise
+            constexpr int NP = WarpSumPad<NACC>::value;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const double wtot = warp_transpose_sum<NACC>(acc);
+            const int slot = warp_sum_slot<NACC>(lane);
+            if ((lane & (32 / NP - 1)) == 0) red[warp * NP + slot] = wtot;      // one of the lanes holding this slot
+            __syncthreads();
+            if (threadIdx.x < kAccStride) {
+                double r = 0.0;
+                if (threadIdx.x < NACC) {
+                    const double* q = red + threadIdx.x;
+                    r = ((q[0] + q[NP]) + (q[2 * NP] + q[3 * NP])) + ((q[4 * NP] + q[5 * NP]) + (q[6 * NP] + q[7 * NP]));
+                }
+#pragma unroll
+                for (int q = 0; q < kClusterMaxCtas; ++q)
+                    if (q < (int)n_ctas) st_remote_shared_f64(&rows[p & 1][cta][threadIdx.x], (uint32_t)q, r);
+            }
+        }
+        if (trace) trace[p * 8 + 3] = clock64();
         cluster_barrier();                       // every CTA's row of this pass is complete and visible
+        if (trace) trace[p * 8 + 4] = clock64();
 
         if (threadIdx.x < kAccStride) {
             double part[kClusterMaxCtas];
 #pragma unroll
             for (int q = 0; q < kClusterMaxCtas; ++q)
-                part[q] = (q < (int)n_ctas && threadIdx.x < NACC) ? ld_remote_shared_f64(&rows[p & 1][threadIdx.x], (uint32_t)q) : 0.0;
-            double tot = 0.0;
+                part[q] = (q < (int)n_ctas) ? rows[p & 1][q][threadIdx.x] : 0.0;
+            // pairwise, in an order that depends on nothing but the ranks: the same bits in every CTA
 #pragma unroll
-            for (int q = 0; q < kClusterMaxCtas; ++q) tot += part[q];      // rank order: the same bits in every CTA
-            sums_sh[threadIdx.x] = tot;
+            for (int w = 1; w < kClusterMaxCtas; w *= 2) {
+#pragma unroll
+                for (int q = 0; q + w < kClusterMaxCtas; q += 2 * w) part[q] += part[q + w];
+            }
+            sums_sh[threadIdx.x] = part[0];
             if (threadIdx.x < kMaxK) { o_gamma[threadIdx.x] = 0.0; o_beta[threadIdx.x] = 0.0; o_sv[threadIdx.x] = 0.0; }
             if (threadIdx.x < 4) o_ms[threadIdx.x] = 0.0;
             if (threadIdx.x == 0) o_rank[0] = 0;
         }
         __syncthreads();
+        if (trace) trace[p * 8 + 5] = clock64();
 
         const int row = final_pass ? 0 : t - 1;
         SolveArgs sv = {};
@@ -185,17 +292,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
         sv.do_solve = final_pass ? 0 : 1;
         sv.final_price = final_pass ? 1 : 0;
         sv.spec = a.solve.spec;
-        if (final_pass) {
-            sv.y_scale = 1.0; sv.mu_ref = 0.0; sv.sigma_ref = 1.0;
-        } else {
-            const SolverTab tb = a.solve_tab[row];
-            sv.y_scale = tb.y_scale; sv.mu_ref = tb.mu; sv.sigma_ref = tb.sigma;
-        }
+        sv.y_scale = tb.y_scale; sv.mu_ref = tb.mu; sv.sigma_ref = tb.sigma;
         sv.gamma = o_gamma; sv.beta = o_beta; sv.sv = o_sv; sv.mean_std = o_ms; sv.rank = o_rank; sv.price = o_price;
         sv.n_batch = 1;
+        // (the scalar routine inlined with its matrices in registers, as in the dedicated solve kernel)
         solve_block<K, false>(sv, sv, 0u, nullptr);          // ends with a block barrier: o_* are complete
+        if (trace) trace[p * 8 + 6] = clock64();
 
-        if (cta == 0) {
+        if (cta == n_ctas - 1) {                  // the CTA with the shortest slice keeps the books
             if (final_pass) {
                 if (threadIdx.x == 0) {
                     a.solve.price[0] = o_price[0];
@@ -210,6 +314,9 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
                 if (threadIdx.x == 0 && a.solve.rank) a.solve.rank[row] = o_rank[0];
             }
         }
+        td = tr;
+        tr = tr_next;
+        if (trace) trace[p * 8 + 7] = clock64();
     }
     // the state goes back to global memory once (cashflows are an output of the sweep)
     UT* const Ug = static_cast<UT*>(a.U) + p_lo;
@@ -290,6 +397,11 @@ static cudaError_t launch_cluster_t(const SweepArgs& a, cudaStream_t s) {
     return cudaLaunchKernelEx(&cfg, lsm_cluster_kernel<XT, UT, D>, a);
 }
 
+// Degrees 0..5 only: there the register-resident scalar routine is the solve (as in the dedicated solve kernel).  From
+// degree 6 on the warp-cooperative routine is, and measured on B200 the chain is faster at every path count
+// (profiles/r2_cluster_vs_chain.md), so those sets stay on it.
+constexpr int kClusterMaxDegree = 5;
+
 template <typename XT, typename UT>
 static cudaError_t launch_cluster_d(int degree, const SweepArgs& a, cudaStream_t s) {
     switch (degree) {
@@ -299,11 +411,6 @@ static cudaError_t launch_cluster_d(int degree, const SweepArgs& a, cudaStream_t
         case 3: return launch_cluster_t<XT, UT, 3>(a, s);
         case 4: return launch_cluster_t<XT, UT, 4>(a, s);
         case 5: return launch_cluster_t<XT, UT, 5>(a, s);
-        case 6: return launch_cluster_t<XT, UT, 6>(a, s);
-        case 7: return launch_cluster_t<XT, UT, 7>(a, s);
-        case 8: return launch_cluster_t<XT, UT, 8>(a, s);
-        case 9: return launch_cluster_t<XT, UT, 9>(a, s);
-        case 10: return launch_cluster_t<XT, UT, 10>(a, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -317,11 +424,6 @@ static int64_t cluster_capacity_d(int degree) {
         case 3: return cluster_plan_t<XT, UT, 3>().max_paths;
         case 4: return cluster_plan_t<XT, UT, 4>().max_paths;
         case 5: return cluster_plan_t<XT, UT, 5>().max_paths;
-        case 6: return cluster_plan_t<XT, UT, 6>().max_paths;
-        case 7: return cluster_plan_t<XT, UT, 7>().max_paths;
-        case 8: return cluster_plan_t<XT, UT, 8>().max_paths;
-        case 9: return cluster_plan_t<XT, UT, 9>().max_paths;
-        case 10: return cluster_plan_t<XT, UT, 10>().max_paths;
     }
     return 0;
 }

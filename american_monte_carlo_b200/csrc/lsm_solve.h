@@ -38,6 +38,16 @@
 
 namespace amc {
 
+// 1 / sqrt(x): the device's rsqrt (<= 1 ulp, no division, no separate square root) -- the host build of this header (CPU
+// test tier) has no such instruction and divides
+AMC_HD double amc_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 constexpr int kMaxDegree = 10;           // notebook uses degree 10; plots.py sweeps 0..10
 constexpr int kMaxK = kMaxDegree + 1;
 
@@ -51,6 +61,8 @@ struct SolveSpec {
     double scaling_factor;    // regression_estimate(..., scaling_factor=2)
     double n_paths;           // GLOBAL number of paths (all ranks) -- enters numpy's rcond = eps*max(P,k)
     int warp_solve;           // device only: try the warp-cooperative routine first (lsm_solve_warp.cuh)
+    double inv_n_paths;       // 1 / n_paths, computed once on the host (0: not set, the solve divides itself): the division
+                              // heads the dependent chain of every solve of a sweep
 };
 
 struct SolveResult {
@@ -189,7 +201,7 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
                         double sigma_ref, SolveResult* out) {
     constexpr int D = K - 1;
     const double P = spec.n_paths;
-    const double invP = 1.0 / P;
+    const double invP = (spec.inv_n_paths > 0.0) ? spec.inv_n_paths : 1.0 / P;
     AMC_UNROLL
     for (int i = 0; i < kMaxK; ++i) out->gamma[i] = out->beta[i] = out->sv[i] = 0.0;
     out->sweeps = 0;
@@ -226,6 +238,10 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
     for (int i = 0; i < K; ++i) Linv[i] = 0.0;
     int kint = K;
     const double pivot_tol = 2e-14;
+    // pivot loss = max_j G_jj / pivot_j, kept as the (numerator, denominator) pair that maximises it and divided once at
+    // the end: the division is a diagnostic, the factorisation's dependent chain should not carry it
+    double loss_num = 1.0, loss_den = 1.0;
+    bool loss_overflow = false;
     AMC_UNROLL
     for (int j = 0; j < K; ++j) {
         if (kint == K) {
@@ -238,14 +254,17 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
                 // exactly degenerate column: the fit is truncated to the first j monomials WITHOUT numpy's singular-
                 // value rule having been applied to A, so the loss is reported (the host warns from 1e12 on).
                 if (j >= 2 && P > (double)K) {
-                    const double loss = (djj > 0.0) ? Hn[2 * j] / djj : 1e300;
-                    if (loss > out->pivot_loss) out->pivot_loss = loss;
+                    if (djj > 0.0) {
+                        if (Hn[2 * j] * loss_den > loss_num * djj) { loss_num = Hn[2 * j]; loss_den = djj; }
+                    } else {
+                        loss_overflow = true;
+                    }
                 }
             } else {
-                const double ljj = sqrt(djj);
-                const double inv = 1.0 / ljj;
-                const double loss = Hn[2 * j] / djj;
-                if (loss > out->pivot_loss) out->pivot_loss = loss;
+                // one reciprocal square root per pivot (L_jj = pivot * rsqrt(pivot)), multiplications everywhere else
+                const double inv = amc_rsqrt(djj);
+                const double ljj = djj * inv;
+                if (Hn[2 * j] * loss_den > loss_num * djj) { loss_num = Hn[2 * j]; loss_den = djj; }
                 L[j][j] = ljj;
                 Linv[j] = inv;
                 AMC_UNROLL
@@ -258,6 +277,7 @@ AMC_HD void lsm_solve_t(const SolveSpec& spec, const double* h, const double* g,
             }
         }
     }
+    out->pivot_loss = loss_overflow ? 1e300 : loss_num / loss_den;
     out->k_internal = kint;
     if (kint == 0) { out->rank = 0; return; }         // no paths / all-NaN input
 

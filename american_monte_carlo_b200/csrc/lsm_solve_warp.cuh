@@ -32,7 +32,7 @@ __device__ bool lsm_solve_warp(const SolveSpec& spec, const double* hsum /* [2d]
     const int lane = threadIdx.x & 31;
     if (spec.want_svd || D == 0 || !spec.warp_solve) return false;
     const double P = spec.n_paths;
-    const double invP = 1.0 / P;
+    const double invP = (spec.inv_n_paths > 0.0) ? spec.inv_n_paths : 1.0 / P;
     for (int m = lane; m <= 2 * D; m += 32) sh.Hn[m] = (m == 0 ? P : hsum[m - 1]) * invP;
     const double bi = (lane < K) ? gsum[lane] * y_scale * invP : 0.0;
     __syncwarp();
@@ -57,9 +57,9 @@ __device__ bool lsm_solve_warp(const SolveSpec& spec, const double* hsum /* [2d]
             if (!(djj > pivot_tol * sh.Hn[2 * j])) {
                 ok = 0;
             } else {
-                const double ljj = sqrt(djj);
-                inv = 1.0 / ljj;
-                pivot_loss = sh.Hn[2 * j] / djj;
+                inv = amc_rsqrt(djj);                       // as the scalar routine: L_jj = pivot * rsqrt(pivot)
+                const double ljj = djj * inv;
+                pivot_loss = sh.Hn[2 * j] / djj;            // per-lane, off the other lanes' critical path
                 sh.L[j][j] = ljj;
                 sh.Linv[j] = inv;
             }

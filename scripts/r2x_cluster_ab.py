@@ -17,7 +17,7 @@ def main():
     n = 50
     cases = [("float64", "float64", "Power", 3, {}), ("float32", "float32", "Power", 3, {}),
              ("float64", "float64", "Chebyshev", 4, {}), ("float64", "float64", "Laguerre", 8, dict(scaling=True))]
-    for P in (10_000, 25_000, 50_000, 100_000, 140_000, 250_000):
+    for P in (10_000, 25_000, 50_000, 75_000, 100_000, 140_000):
         for dtype, state, basis, deg, kw in cases:
             dp = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, n, P, rng="philox", seed=7, dtype=dtype)
             ms, kinds, price = [], set(), None

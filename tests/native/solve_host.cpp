@@ -16,6 +16,8 @@ extern "C" int amc_test_lsm_solve(int degree, int basis, int scaling, int want_s
     spec.want_svd = want_svd;
     spec.scaling_factor = scaling_factor;
     spec.n_paths = n_paths;
+    spec.warp_solve = 0;
+    spec.inv_n_paths = n_paths > 0.0 ? 1.0 / n_paths : 0.0;
     amc::SolveResult res;
     amc::lsm_solve(spec, h, g, y_scale, mu_ref, sigma_ref, &res);
     for (int i = 0; i <= degree; ++i) { gamma[i] = res.gamma[i]; beta[i] = res.beta[i]; sv[i] = res.sv[i]; }
