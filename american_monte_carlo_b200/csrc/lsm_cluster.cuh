@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
         mbar_init(&full[1], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    cluster_barrier();                           // every CTA of the cluster is running: its shared memory may be written
     // thread 0: fetch column t into its buffer
     auto fetch = [&](int t) {
         if (cnt == 0) return;

@@ -1,5 +1,5 @@
 """Instruction mix of every kernel in libamc.so (cuobjdump -sass), the evidence for what each kernel runs on:
-UBLKCP (1-D TMA bulk copies) / SYNCS (mbarrier) in the sweep kernels, LDGSTS (cp.async) in the injected-normals path
+UBLKCP (1-D TMA bulk copies) / SYNCS (mbarrier) in the sweep kernels, UCGABAR (hardware cluster barrier) in the one-cluster kernel, LDGSTS (cp.async) in the injected-normals path
 kernel, DFMA / DADD / DMUL (FP64 pipe), MUFU + I2FP/F2F (XU pipe) in the generators; no tensor-core mnemonics by design.
 
     python profiles/sass_digest.py > profiles/r2_sass_digest.txt          (build container, no GPU needed)
@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "american_monte_carlo_b200", "libamc.so")
-WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "LDGSTS", "DFMA", "DADD", "DMUL", "DSETP", "MUFU", "I2FP", "F2F", "FFMA", "IMAD.WIDE",
+WATCH = ["UBLKCP", "UTMALDG", "UCGABAR", "SYNCS", "LDGSTS", "DFMA", "DADD", "DMUL", "DSETP", "MUFU", "I2FP", "F2F", "FFMA", "IMAD.WIDE",
          "LOP3", "LDS", "STS", "LDG", "STG", "LDL", "STL", "ATOM", "RED", "SHFL", "BAR", "UTCHMMA", "HMMA", "LDTM"]
 
 
@@ -35,11 +35,12 @@ def main():
             op = m.group(1)
             cur["_total"] += 1
             for w in WATCH:
-                if op == w or op.startswith(w + "."):
+                if op == w or op.startswith(w + ".") or (w == "UCGABAR" and op.startswith("UCGABAR")):
                     cur[w] += 1
     names = demangle(list(kernels))
     want = sys.argv[1:] or ["lsm_sweep_kernel<float, float, 3, false>", "lsm_sweep_kernel<float, float, 3, true>",
-                            "lsm_sweep_kernel<double, double, 3, false>", "lsm_step_tma_kernel<float, float, 3>",
+                            "lsm_sweep_kernel<double, double, 3, false>", "lsm_cluster_kernel<double, double, 3>",
+                            "lsm_cluster_kernel<float, float, 3>", "lsm_step_tma_kernel<float, float, 3>",
                             "lsm_step_tma_kernel<float, double, 3>", "lsm_step_tma_kernel<double, double, 3>",
                             "lsm_step_tma_kernel<float, float, 8>", "lsm_solve_kernel<4>", "lsm_solve_kernel<9>",
                             "philox_quads_f32_kernel<10, true, 6>", "philox_quads_f32_kernel<7, true, 6>", "philox_paths_f64_kernel",
