@@ -10,15 +10,17 @@
 //     per CTA (cp.async.bulk + mbarrier) issued a whole pass before it is needed: column t-2 replaces column t as soon as
 //     the pass of step t is through its loop, and lands while that pass reduces and solves;
 //   * pass t: decide(t) + moments(t-1) from shared memory (the arithmetic of the step kernel: path_step /
-//     fast_path_step), block reduction into this CTA's row, ONE barrier.cluster, then EVERY CTA gathers the rows of all
-//     CTAs through distributed shared memory in rank order and runs the k x k solve itself (same inputs, same code, same
-//     bits) -- no broadcast, no second barrier; rows are double-buffered by pass parity;
-//   * CTA 0 copies the regression diagnostics of the step and, after the last pass, the price to global memory; every CTA
-//     writes its slice of the state back once at the end.
+//     fast_path_step, 8/4/2 paths in flight per thread), block reduction by recursive halving into this CTA's row, which
+//     the CTA PUSHES into the shared memory of every CTA of the cluster (st.shared::cluster), ONE barrier.cluster, then
+//     EVERY CTA adds the rows pairwise in rank order and runs the k x k solve itself (same inputs, same code, same bits) --
+//     no broadcast, no second barrier; rows are double-buffered by pass parity;
+//   * the last CTA (shortest slice) copies the regression diagnostics of the step and, after the last pass, the price to
+//     global memory; every CTA writes its slice of the state back once at the end.
 //
 // No spin loops, no global flags: the only waits are mbarriers on the CTA's own copies and the hardware cluster barrier.
-// Capacity is what 16 x ~215 KB of shared memory hold (2 columns + state per path): ~140k paths f64/f64, ~280k f32/f32;
-// larger sets take the launch chain.
+// Capacity is what 16 x ~215 KB of shared memory hold (2 columns + state per path): ~146k paths f64/f64, ~290k f32/f32;
+// the default policy (api.cu) stops at 131072 paths, where the launch chain's 148 SMs catch up with the cluster's 16
+// (profiles/r2_cluster_vs_chain.md), and at degree 5 (beyond, the warp-cooperative solve is used and the chain is faster).
 #pragma once
 #include <type_traits>
 
