@@ -53,6 +53,12 @@ CLUSTER_CASES = [
     ("put_f32paths", 30011, 20, "float32", "float64", dict(), "Power", 3, dict()),
     ("put_f32state", 30011, 20, "float32", "float32", dict(), "Power", 3, dict()),
     ("put_cheb4_unscaled_f64", 25000, 12, "float64", "float64", dict(), "Chebyshev", 4, dict()),   # rank-truncated steps
+    # the remaining degrees the cluster kernel is instantiated for (7 and 16 accumulators: other reduction widths)
+    ("put_deg2_f64", 4097, 9, "float64", "float64", dict(), "Power", 2, dict()),
+    ("put_deg5_scaled_f64", 33333, 8, "float64", "float64", dict(), "Legendre", 5, dict(scaling=True)),
+    ("call_deg5_barrier_f32state", 8191, 6, "float32", "float32", dict(opt="Call", K=35.0, barrier=38.0), "Chebyshev", 5,
+     dict(scaling=True)),
+    ("european_deg2_f32paths", 2049, 5, "float32", "float64", dict(ex="European"), "Legendre", 2, dict()),
 ]
 
 _CLUSTER_WORKER = r"""
