@@ -59,6 +59,9 @@ CLUSTER_CASES = [
     ("call_deg5_barrier_f32state", 8191, 6, "float32", "float32", dict(opt="Call", K=35.0, barrier=38.0), "Chebyshev", 5,
      dict(scaling=True)),
     ("european_deg2_f32paths", 2049, 5, "float32", "float64", dict(ex="European"), "Legendre", 2, dict()),
+    # one and two time steps: no column is fetched ahead / exactly one is
+    ("put_one_step", 5000, 1, "float64", "float64", dict(), "Power", 3, dict()),
+    ("put_two_steps", 5000, 2, "float64", "float64", dict(), "Power", 3, dict()),
 ]
 
 _CLUSTER_WORKER = r"""
