@@ -1098,7 +1098,7 @@ static int lsm_sweep(amc_ctx* c, const amc_paths* p, const amc_lsm_spec* specs, 
         if (cap < 0) cap = cluster_sweep_capacity(dtype, sf32, D);
         // what the cluster's shared memory holds is more than what it prices faster than the chain: the 16 SMs of the
         // cluster stream a pass at FP64-pipe speed, the chain's 148 do not care (profiles/r2_cluster_vs_chain.md)
-        static const long long opt_cluster_max = getenv("AMC_CLUSTER_MAX_PATHS") ? atoll(getenv("AMC_CLUSTER_MAX_PATHS")) : 131072;
+        static const long long opt_cluster_max = getenv("AMC_CLUSTER_MAX_PATHS") ? atoll(getenv("AMC_CLUSTER_MAX_PATHS")) : 147456;
         cluster = P <= cap && P <= opt_cluster_max;
     }
     const bool persistent = C == 1 && (opt_persistent || p->lean || cluster) && (!exchange || c->transport == 2);

@@ -11,15 +11,17 @@
 //     the pass of step t is through its loop, and lands while that pass reduces and solves;
 //   * pass t: decide(t) + moments(t-1) from shared memory (the arithmetic of the step kernel: path_step /
 //     fast_path_step, 8/4/2 paths in flight per thread), block reduction by recursive halving into this CTA's row, which
-//     the CTA PUSHES into the shared memory of every CTA of the cluster (st.shared::cluster), ONE barrier.cluster, then
-//     EVERY CTA adds the rows pairwise in rank order and runs the k x k solve itself (same inputs, same code, same bits) --
-//     no broadcast, no second barrier; rows are double-buffered by pass parity;
+//     the CTA PUSHES into the shared memory of every CTA of the cluster with asynchronous remote stores that complete the
+//     transaction count of the receiver's mbarrier (st.async ... mbarrier::complete_tx::bytes); a CTA waits on its OWN
+//     mbarrier only -- no cluster-wide barrier inside the sweep -- then adds the rows pairwise in rank order and runs the
+//     k x k solve itself (same inputs, same code, same bits: no broadcast); rows are double-buffered by pass parity;
 //   * the last CTA (shortest slice) copies the regression diagnostics of the step and, after the last pass, the price to
 //     global memory; every CTA writes its slice of the state back once at the end.
 //
-// No spin loops, no global flags: the only waits are mbarriers on the CTA's own copies and the hardware cluster barrier.
+// No spin loops, no global flags: the only waits are the CTA's own mbarriers (column copies, rows) and the hardware cluster
+// barrier at the start and the end of the kernel.
 // Capacity is what 16 x ~215 KB of shared memory hold (2 columns + state per path): ~146k paths f64/f64, ~290k f32/f32;
-// the default policy (api.cu) stops at 131072 paths, where the launch chain's 148 SMs catch up with the cluster's 16
+// the default policy (api.cu) stops at 147456 paths, where the launch chain's 148 SMs catch up with the cluster's 16
 // (profiles/r2_cluster_vs_chain.md), and at degree 5 (beyond, the warp-cooperative solve is used and the chain is faster).
 #pragma once
 #include <type_traits>
@@ -48,11 +50,16 @@ __device__ __forceinline__ uint32_t cluster_cta_count() {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// store into the shared memory of CTA `cta` of the cluster, at the address `local` has in this CTA
-__device__ __forceinline__ void st_remote_shared_f64(double* local, uint32_t cta, double v) {
-    uint32_t remote;
+// asynchronous store of 8 bytes into the shared memory of CTA `cta` of the cluster (at the address `local` has in this
+// CTA) that completes 8 bytes of the pending transaction of THAT CTA's mbarrier `local_bar`: the receiver waits on its
+// own barrier -- no cluster-wide barrier, no fence
+__device__ __forceinline__ void st_async_remote_f64(double* local, uint64_t* local_bar, uint32_t cta, double v) {
+    uint32_t remote, remote_bar;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr(local)), "r"(cta));
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_bar) : "r"(smem_addr(local_bar)), "r"(cta));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
 }
 
 // Sum N per-lane values over the 32 lanes of a warp by recursive halving: at every stage a lane hands half of its vector
@@ -106,9 +113,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
     constexpr int NACC = 3 * D + 1;
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ double red[(kClusterThreads / 32) * WarpSumPad<NACC>::value];
-    // rows[p & 1][q] = CTA q's partial sums of pass p, PUSHED here by CTA q before the pass's cluster barrier (every CTA
-    // holds all rows: the remote-store latency is spent inside the barrier, the reads after it are local)
+    // rows[p & 1][q] = CTA q's partial sums of pass p, PUSHED here by CTA q with asynchronous remote stores that complete
+    // the transaction count of rowbar[p & 1] (every CTA holds all rows and waits on its own barrier only; a CTA can push
+    // the rows of pass p + 2 only after every CTA has read those of pass p -- it needs everybody's rows of pass p + 1 first)
     __shared__ __align__(16) double rows[2][kClusterMaxCtas][kAccStride];
+    __shared__ uint64_t rowbar[2];
     __shared__ double sums_sh[kAccStride];
     __shared__ double o_gamma[kMaxK], o_beta[kMaxK], o_sv[kMaxK], o_ms[4], o_price[1];
     __shared__ int o_rank[1];
@@ -129,8 +138,11 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
     if (threadIdx.x == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
+        mbar_init(&rowbar[0], 1);
+        mbar_init(&rowbar[1], 1);
         mbar_fence_init();
     }
+    for (int i = threadIdx.x; i < 2 * kClusterMaxCtas * kAccStride; i += kClusterThreads) (&rows[0][0][0])[i] = 0.0;
     cluster_barrier();                           // every CTA of the cluster is running: its shared memory may be written
     // thread 0: fetch column t into its buffer
     auto fetch = [&](int t) {
@@ -259,16 +271,19 @@ __global__ void __launch_bounds__(kClusterThreads, 1) lsm_cluster_kernel(const _
                     const double* q = red + threadIdx.x;
                     r = ((q[0] + q[NP]) + (q[2 * NP] + q[3 * NP])) + ((q[4 * NP] + q[5 * NP]) + (q[6 * NP] + q[7 * NP]));
                 }
+                if (threadIdx.x == 0) mbar_expect_tx(&rowbar[p & 1], n_ctas * (uint32_t)NACC * 8u);    // what this CTA receives
+                if (threadIdx.x < NACC) {
 #pragma unroll
-                for (int q = 0; q < kClusterMaxCtas; ++q)
-                    if (q < (int)n_ctas) st_remote_shared_f64(&rows[p & 1][cta][threadIdx.x], (uint32_t)q, r);
+                    for (int q = 0; q < kClusterMaxCtas; ++q)
+                        if (q < (int)n_ctas) st_async_remote_f64(&rows[p & 1][cta][threadIdx.x], &rowbar[p & 1], (uint32_t)q, r);
+                }
             }
         }
         if (trace) trace[p * 8 + 3] = clock64();
-        cluster_barrier();                       // every CTA's row of this pass is complete and visible
-        if (trace) trace[p * 8 + 4] = clock64();
 
         if (threadIdx.x < kAccStride) {
+            mbar_wait(&rowbar[p & 1], (uint32_t)(p >> 1) & 1u);     // every CTA's row of this pass has landed here
+            if (trace) trace[p * 8 + 4] = clock64();
             double part[kClusterMaxCtas];
 #pragma unroll
             for (int q = 0; q < kClusterMaxCtas; ++q)

@@ -128,7 +128,7 @@ def test_cluster_kernel_equals_launch_chain_and_oracle(amc, tmp_path):
 
 
 def test_cluster_kernel_capacity_edge(libamc_path):
-    """Path counts around what one cluster's shared memory holds (AMC_CLUSTER_MAX_PATHS lifts the default cut at 131072
+    """Path counts around what one cluster's shared memory holds (AMC_CLUSTER_MAX_PATHS lifts the default cut at 147456
     paths, which is a speed threshold, not a capacity): the largest set the cluster kernel takes and the first one that
     goes to the launch chain agree with the oracle alike (3 steps keep the oracle quick)."""
     import subprocess
@@ -155,10 +155,10 @@ def test_cluster_kernel_capacity_edge(libamc_path):
 
 
 def test_cluster_kernel_default_threshold(amc):
-    """By default the cluster kernel takes sets of up to 131072 paths (where it is at least as fast as the chain on B200:
-    profiles/r2_cluster_vs_chain.md)."""
-    for P, kind in ((131072, 2), (131073, 0)):
-        dp = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 4, P, rng="philox", seed=11)
+    """By default the cluster kernel takes sets of up to 147456 paths (where it is at least as fast as the chain on B200:
+    profiles/r2_cluster_vs_chain.md); float paths, whose capacity is beyond that, show the threshold."""
+    for P, kind in ((147456, 2), (147457, 0)):
+        dp = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 4, P, rng="philox", seed=11, dtype="float32")
         res = amc.lsm_price(dp, 40.0, 0.06, 0.25, "Put", None, "American", "Power", 3)
         assert res.timing["sweep_kind"] == kind, (P, res.timing)
         dp.free()
