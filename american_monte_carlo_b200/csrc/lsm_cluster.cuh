@@ -24,6 +24,7 @@
 // the default policy (api.cu) stops at 147456 paths, where the launch chain's 148 SMs catch up with the cluster's 16
 // (profiles/r2_cluster_vs_chain.md), and at degree 5 (beyond, the warp-cooperative solve is used and the chain is faster).
 #pragma once
+#include <mutex>
 #include <type_traits>
 
 #include "kernels.h"
@@ -350,15 +351,12 @@ struct ClusterPlan {
 };
 
 template <typename XT, typename UT, int D>
-static const ClusterPlan& cluster_plan_t() {
-    static ClusterPlan plan;
-    static bool done = false;
-    if (done) return plan;
-    done = true;
+static ClusterPlan make_cluster_plan(int dev) {
+    ClusterPlan plan;
     auto kernel = lsm_cluster_kernel<XT, UT, D>;
     cudaFuncAttributes fa;
-    int dev = 0, optin = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaFuncGetAttributes(&fa, kernel) != cudaSuccess ||
+    int optin = 0;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess ||
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
         cudaGetLastError();
         return plan;
@@ -393,6 +391,27 @@ static const ClusterPlan& cluster_plan_t() {
         cudaGetLastError();
     }
     return plan;
+}
+
+// the plan of the CURRENT device (function attributes are per device), made on first use; safe from several host threads
+template <typename XT, typename UT, int D>
+static const ClusterPlan& cluster_plan_t() {
+    constexpr int kMaxDevices = 64;
+    static std::mutex mu;
+    static ClusterPlan plans[kMaxDevices];
+    static bool made[kMaxDevices] = {};
+    static const ClusterPlan none;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        cudaGetLastError();
+        return none;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!made[dev]) {
+        plans[dev] = make_cluster_plan<XT, UT, D>(dev);
+        made[dev] = true;
+    }
+    return plans[dev];
 }
 
 template <typename XT, typename UT, int D>
