@@ -130,13 +130,15 @@ def test_cluster_kernel_equals_launch_chain_and_oracle(amc, tmp_path):
 def test_cluster_kernel_capacity_edge(libamc_path):
     """Path counts around what one cluster's shared memory holds (AMC_CLUSTER_MAX_PATHS lifts the default cut at 147456
     paths, which is a speed threshold, not a capacity): the largest set the cluster kernel takes and the first one that
-    goes to the launch chain agree with the oracle alike (3 steps keep the oracle quick)."""
+    goes to the launch chain agree with the oracle alike (3 steps keep the oracle quick).  Where the capacity ends depends
+    on the cluster the device grants (16 CTAs: 145408 f64 paths at degree 3; 8 CTAs: half of that) -- the test asks for one
+    threshold somewhere between the first and the last size."""
     import subprocess
     code = (
         "import numpy as np, american_monte_carlo_b200 as amc\n"
         "from oracle import lsm_oracle as orc\n"
         "n = 3; kinds = []\n"
-        "for P in (131_072, 140_000, 145_920, 145_921, 150_000, 160_000):\n"
+        "for P in (60_000, 72_000, 74_000, 131_072, 145_408, 145_409, 150_000, 160_000):\n"
         "    Z = np.random.default_rng(P).standard_normal((P, n))\n"
         "    paths = orc.paths_from_normals(Z, 36.0, 0.06, 0.2, 1.0)\n"
         "    want = orc.lsm_backward(paths, 40.0, 0.06, 1.0 / n, 'Put', None, 'American', 'Power', 3, keep_continuation=False)\n"
@@ -156,12 +158,15 @@ def test_cluster_kernel_capacity_edge(libamc_path):
 
 def test_cluster_kernel_default_threshold(amc):
     """By default the cluster kernel takes sets of up to 147456 paths (where it is at least as fast as the chain on B200:
-    profiles/r2_cluster_vs_chain.md); float paths, whose capacity is beyond that, show the threshold."""
-    for P, kind in ((147456, 2), (147457, 0)):
+    profiles/r2_cluster_vs_chain.md); float paths, whose capacity in a 16-CTA cluster is beyond that, show the threshold."""
+    kinds = []
+    for P in (60_000, 147_000, 147_456, 147_457):
         dp = amc.generate_asset_paths(36.0, 0.06, 0.2, 1.0, 4, P, rng="philox", seed=11, dtype="float32")
-        res = amc.lsm_price(dp, 40.0, 0.06, 0.25, "Put", None, "American", "Power", 3)
-        assert res.timing["sweep_kind"] == kind, (P, res.timing)
+        kinds.append(amc.lsm_price(dp, 40.0, 0.06, 0.25, "Put", None, "American", "Power", 3).timing["sweep_kind"])
         dp.free()
+    assert kinds[0] == 2 and kinds[3] == 0 and kinds == sorted(kinds, reverse=True), kinds
+    if kinds[1] == 2:                    # the capacity reaches the threshold (16-CTA cluster): the cut is exactly there
+        assert kinds[2] == 2, kinds
 
 
 def test_launch_chain_on_ragged_small_shapes(libamc_path):
