@@ -440,6 +440,7 @@ constexpr int kClusterMaxDegree = 5;
 
 template <typename XT, typename UT>
 static cudaError_t launch_cluster_d(int degree, const SweepArgs& a, cudaStream_t s) {
+    if (degree < 0 || degree > kClusterMaxDegree) return cudaErrorInvalidValue;
     switch (degree) {
         case 0: return launch_cluster_t<XT, UT, 0>(a, s);
         case 1: return launch_cluster_t<XT, UT, 1>(a, s);
@@ -453,6 +454,7 @@ static cudaError_t launch_cluster_d(int degree, const SweepArgs& a, cudaStream_t
 
 template <typename XT, typename UT>
 static int64_t cluster_capacity_d(int degree) {
+    if (degree < 0 || degree > kClusterMaxDegree) return 0;
     switch (degree) {
         case 0: return cluster_plan_t<XT, UT, 0>().max_paths;
         case 1: return cluster_plan_t<XT, UT, 1>().max_paths;
